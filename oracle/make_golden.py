@@ -1,0 +1,189 @@
+"""TEST INFRASTRUCTURE ONLY -- regenerate tests/golden/*.npz from the reference itself.
+
+Run in the BUILD container (the reference is not present on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py [/root/reference]
+
+For every case it (1) runs the unmodified reference (imported from the path given), (2) runs
+``oracle/parla_oracle.py`` on the same inputs and seeds, (3) asserts the two agree to round-off
+(the numbers printed), and (4) stores the REFERENCE's outputs plus whatever is needed to rebuild
+the inputs (seeds; the sketching operator in index form) as a small fixture.  This is what pins
+the oracle (see the header of parla_oracle.py).
+"""
+import hashlib
+import os
+import sys
+import warnings
+
+import numpy as np
+import scipy.linalg as sla
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+np.NaN = np.nan            # numpy-2 shim needed by the reference's QB2 (qb.py:468)
+warnings.filterwarnings("ignore")
+
+import parla as rla                                             # noqa: E402  (the reference)
+import parla.comps.sketchers.oblivious as rsko                  # noqa: E402
+import parla.utils.linalg_wrappers as rulaw                     # noqa: E402
+import parla.tests.matmakers as rmm                             # noqa: E402
+from oracle import parla_oracle as orc                          # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+class Tape:
+    """Wraps a sketch-operator generator and records every operator it returns."""
+
+    def __init__(self, gen):
+        self.gen, self.ops = gen, []
+
+    def __call__(self, n_rows, n_cols, rng):
+        S = self.gen(n_rows, n_cols, rng)
+        self.ops.append(S)
+        return S
+
+
+def lsq_problem(m, n, seed, cond=1.0):
+    """Gaussian A with optional column scaling, b = A x0 + 0.1 noise (SURVEY.md 8d, cfg1 recipe)."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((m, n))
+    if cond != 1.0:
+        A = A * np.logspace(0, np.log10(cond), n)
+    x0 = rng.standard_normal(n)
+    b = A @ x0 + 0.1 * rng.standard_normal(m)
+    return A, b
+
+
+def digest(arr):
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+def spo_case(name, m, n, seed, sketch, mode, delta, sf=4, tol=1e-12, iter_lim=100, cond=1.0,
+             store_S=True, rng_seed=1):
+    A, b = lsq_problem(m, n, seed, cond)
+    ref_gen = Tape(rsko.SkOpSJ(8) if sketch == 'sjlt' else rsko.SkOpGA())
+    orc_gen = Tape(orc.SkOpSJ(8) if sketch == 'sjlt' else orc.SkOpGA())
+    x_ref, log_ref = rla.SPO(ref_gen, sf, mode)(A, b, delta, tol, iter_lim,
+                                               np.random.default_rng(rng_seed), logging=True)
+    x_orc, log_orc = orc.SPO(orc_gen, sf, mode)(A, b, delta, tol, iter_lim,
+                                               np.random.default_rng(rng_seed), logging=True)
+    S_ref, S_orc = ref_gen.ops[0], orc_gen.ops[0]
+    if sketch == 'sjlt':
+        same_S = (S_ref != S_orc).nnz == 0
+        rows, signs, k = orc.sjlt_index_form(S_ref)
+    else:
+        same_S = bool(np.array_equal(S_ref, S_orc))
+    e_x = relerr(x_orc, x_ref)
+    e_err = relerr(log_orc.errors, log_ref.errors)
+    its = (log_ref.errors.size - 1, log_orc.errors.size - 1)
+    print(f"{name:28s} iters ref/orc {its}  |dx|/|x| {e_x:.2e}  d(errors) {e_err:.2e}  S identical {same_S}")
+    assert same_S, "oracle sketch operator differs from the reference's"
+    assert e_x < 1e-11 and its[0] == its[1] and e_err < 1e-6
+    r = A @ x_ref - b
+    fx = dict(m=m, n=n, seed=seed, cond=cond, sketch=sketch, mode=mode, delta=delta, sf=sf, tol=tol,
+              iter_lim=iter_lim, rng_seed=rng_seed, x=x_ref, errors=log_ref.errors,
+              resid_norm=np.linalg.norm(r), A_sha=digest(A), b_sha=digest(b))
+    if sketch == 'sjlt':
+        fx.update(S_sha=digest(rows) + digest(signs), vec_nnz=k)
+        if store_S:
+            fx.update(S_rows=rows.astype(np.int16 if rows.max() < 32768 else np.int32), S_signs=signs)
+    else:
+        fx.update(S_sha=digest(S_ref))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+
+
+def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pass=2, evd=False):
+    rng = np.random.default_rng(seed)
+    if evd:
+        B0 = rmm.rand_low_rank(m, rank, rank, rng)
+        A = B0 @ B0.T
+        A = 0.5 * (A + A.T)
+        n = m
+    else:
+        A = rmm.exponent_spectrum(m, n, rank, rng, 2.0)
+    A_orc = orc.exponent_spectrum(m, n, rank, np.random.default_rng(seed), 2.0) if not evd else A
+    assert relerr(A_orc, A) < 1e-13
+
+    def build(lib, sko, orth):
+        rs = lib.RS1(sko, num_pass, orth, 1)
+        rf = lib.RF1(rs)
+        qb = lib.QB1(rf) if blk is None else lib.QB2(rf, blk, False)
+        return (lib.EVD1(qb) if evd else lib.SVD1(qb)), qb
+
+    ref_alg, ref_qb = build(rla, rsko.SkOpGA(), rulaw.orth)
+    orc_alg, orc_qb = build(orc, orc.SkOpGA(), orc.orth)
+    Q_ref, B_ref = ref_qb(A, k + over, tol, np.random.default_rng(7))
+    Q_orc, B_orc = orc_qb(A, k + over, tol, np.random.default_rng(7))
+    e_qb = relerr(Q_orc @ B_orc, Q_ref @ B_ref)
+    out_ref = ref_alg(A, k, tol, over, np.random.default_rng(7))
+    out_orc = orc_alg(A, k, tol, over, np.random.default_rng(7))
+    if evd:
+        V, lam = out_ref
+        Vo, lamo = out_orc
+        approx_ref, approx_orc = (V * lam) @ V.T, (Vo * lamo) @ Vo.T
+        spec_ref, spec_orc = lam, lamo
+    else:
+        U, s, Vh = out_ref
+        Uo, so, Vho = out_orc
+        approx_ref, approx_orc = (U * s) @ Vh, (Uo * so) @ Vho
+        spec_ref, spec_orc = s, so
+    e_ap = relerr(approx_orc, approx_ref)
+    e_sp = float(np.max(np.abs(spec_orc - spec_ref)) / np.max(np.abs(spec_ref)))
+    print(f"{name:28s} QB cols {Q_ref.shape[1]}  d(QB) {e_qb:.2e}  d(approx) {e_ap:.2e}  d(spec) {e_sp:.2e}")
+    assert Q_ref.shape == Q_orc.shape and e_qb < 1e-10 and e_ap < 1e-10 and e_sp < 1e-12
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), m=m, n=n, rank=rank, k=k, seed=seed,
+                        blk=-1 if blk is None else blk, tol=tol, over=over, num_pass=num_pass,
+                        evd=evd, spec=spec_ref, qb_cols=Q_ref.shape[1],
+                        approx_fro=np.linalg.norm(approx_ref),
+                        err_fro=np.linalg.norm(A - approx_ref), A_sha=digest(A),
+                        approx_probe=approx_ref[::max(1, m // 16), ::max(1, n // 16)])
+
+
+def philox_case():
+    """Known-answer vectors for Philox4x32-10 (Random123 kat_vectors) + oracle stream samples."""
+    from oracle import philox_ref as ph
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = ph.philox4x32_10(np.array([ctr], dtype=np.uint32), np.array(key, dtype=np.uint32))[0]
+        assert tuple(int(v) for v in got) == want, (ctr, key, [hex(int(v)) for v in got])
+    print("philox4x32-10                known-answer vectors OK")
+    np.savez_compressed(os.path.join(OUT, "philox_kat.npz"),
+                        ctr=np.array([c for c, _, _ in kat], dtype=np.uint32),
+                        key=np.array([k for _, k, _ in kat], dtype=np.uint32),
+                        out=np.array([o for _, _, o in kat], dtype=np.uint32))
+
+
+if __name__ == "__main__":
+    philox_case()
+    # sketch-and-precondition least squares: {SJLT, Gaussian} x {qr, svd, chol} x {delta}
+    spo_case("spo_sjlt_qr_600x40", 600, 40, 11, 'sjlt', 'qr', 0.0)
+    spo_case("spo_sjlt_svd_600x40", 600, 40, 11, 'sjlt', 'svd', 0.0)
+    spo_case("spo_sjlt_chol_600x40", 600, 40, 11, 'sjlt', 'chol', 0.0)
+    spo_case("spo_sjlt_qr_ridge_600x40", 600, 40, 12, 'sjlt', 'qr', 0.25)
+    spo_case("spo_sjlt_svd_ridge_600x40", 600, 40, 12, 'sjlt', 'svd', 0.25)
+    spo_case("spo_gauss_qr_500x37", 500, 37, 13, 'gauss', 'qr', 0.0)
+    spo_case("spo_sjlt_qr_cond1e5_2000x64", 2000, 64, 14, 'sjlt', 'qr', 0.0, cond=1e5)
+    spo_case("spo_sjlt_qr_odd_1531x77", 1531, 77, 15, 'sjlt', 'qr', 0.0, sf=3.3)
+    # BASELINE.json configs[0]: 2^16 x 500, SJLT k=8, d=4n, tol 1e-12 (S regenerated + hash-checked)
+    spo_case("spo_cfg1_65536x500", 65536, 500, 0, 'sjlt', 'qr', 0.0, store_S=False)
+    # low-rank path
+    lowrank_case("svd1_qb1_200x50", 200, 50, 15, 15, 21)
+    lowrank_case("svd1_qb2_200x50", 200, 50, 45, 30, 22, blk=8, tol=0.0)
+    lowrank_case("svd1_qb2_tol_200x50", 200, 50, 45, 50, 23, blk=5, tol=1e-3)
+    lowrank_case("svd1_qb1_over_50x200", 50, 200, 15, 10, 24, over=5)
+    lowrank_case("evd1_qb1_120", 120, 120, 12, 12, 25, evd=True)
+    print("golden fixtures written to", OUT)

@@ -1,0 +1,646 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the PARLA randomized-sketching hot path.
+
+A numpy/scipy *restatement* (not a copy) of the algorithms on the path named by
+BASELINE.json:north_star.  Every function cites the reference file:line it follows
+(paths relative to the reference checkout, BallisticLA/parla v0.1.4).
+
+Pinning status: **pinned**.  The reference has no stored golden vectors, so the
+oracle is pinned against outputs of the reference itself, imported in the build container:
+``oracle/make_golden.py`` runs the reference and this oracle on identical inputs, asserts they
+agree (x, residual, per-iteration error history, sketch operators bit-for-bit, low-rank
+factors) and writes the fixtures under ``tests/golden/``.  ``tests/test_oracle_golden.py``
+re-checks the oracle against those committed fixtures without needing the reference.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py`` may import
+this module.  The product path (``parla_b200``) never does.
+"""
+from __future__ import annotations
+
+import math
+import time
+import warnings
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sps
+
+EPS = float(np.finfo(np.float64).eps)
+
+
+# ------------------------------------------------------------------------------------------
+#  Sketching operators            (reference: parla/utils/sketching.py, comps/sketchers/oblivious.py)
+# ------------------------------------------------------------------------------------------
+
+def gaussian_operator(n_rows, n_cols, rng, normalize=True):
+    """Dense iid Gaussian operator.  parla/utils/sketching.py:20-31.
+
+    normalize=True draws N(0, 1/min(n_rows, n_cols)); otherwise N(0, 1).  The numpy
+    Generator call sequence is the reference's, so the stream (and S) is identical.
+    """
+    rng = np.random.default_rng(rng)
+    if not normalize:
+        return rng.standard_normal((n_rows, n_cols))
+    sd = np.sqrt(1.0 / min(n_rows, n_cols))
+    return rng.normal(0.0, sd, (n_rows, n_cols))
+
+
+def sjlt_operator(n_rows, n_cols, rng, vec_nnz=8):
+    """Sparse Johnson-Lindenstrauss operator.  parla/utils/sketching.py:34-80.
+
+    Wide case (n_cols >= n_rows): every column gets ``vec_nnz`` distinct row positions
+    (one ``rng.choice`` per column, :63-65), then ONE ``rng.random(n_cols*vec_nnz)`` draw decides
+    the signs (-1 where the uniform is <= 0.5, :69-70); values are +-1/sqrt(vec_nnz) (:71);
+    result is CSC (:73-74).  Tall case: transpose of the wide construction, CSR (:78-79).
+    """
+    rng = np.random.default_rng(rng)
+    if n_cols < n_rows:
+        return sjlt_operator(n_cols, n_rows, rng, vec_nnz).T.tocsr()
+    k = min(n_cols, vec_nnz)
+    with_replacement = n_rows < k
+    if with_replacement:
+        warnings.warn(f"Can't set {k} nonzeros per column for columns of length {n_rows}. "
+                      "Sampling indices with replacement instead.")
+    picks = [rng.choice(n_rows, k, replace=with_replacement) for _ in range(n_cols)]
+    ri = np.concatenate(picks)
+    ci = np.repeat(np.arange(n_cols), k)
+    sgn = np.ones(n_cols * k)
+    sgn[rng.random(n_cols * k) <= 0.5] = -1.0
+    sgn /= np.sqrt(k)
+    return sps.coo_matrix((sgn, (ri, ci)), shape=(n_rows, n_cols)).tocsc()
+
+
+class SkOpGA:
+    """comps/sketchers/oblivious.py:38-45."""
+
+    def __init__(self, normalize=True):
+        self.normalize = normalize
+
+    def __call__(self, n_rows, n_cols, rng):
+        return gaussian_operator(n_rows, n_cols, rng, self.normalize)
+
+
+class SkOpSJ:
+    """comps/sketchers/oblivious.py:48-55."""
+
+    def __init__(self, vec_nnz=8):
+        self.vec_nnz = vec_nnz
+
+    def __call__(self, n_rows, n_cols, rng):
+        return sjlt_operator(n_rows, n_cols, rng, self.vec_nnz)
+
+
+def sjlt_index_form(S):
+    """Fixed-nnz index form of a wide SJLT: (rows[int32, n_cols x k], signs[int8, n_cols x k], k).
+
+    This is the layout the CUDA path consumes (SURVEY.md 8b "Injected S").  Requires every
+    column to hold the same number of stored entries, which the construction guarantees when
+    sampling without replacement.
+    """
+    S = sps.csc_matrix(S)
+    counts = np.diff(S.indptr)
+    k = int(counts[0])
+    if not np.all(counts == k):
+        raise ValueError("not a fixed-nnz-per-column operator")
+    rows = S.indices.reshape(-1, k).astype(np.int32)
+    signs = np.sign(S.data).reshape(-1, k).astype(np.int8)
+    return rows, signs, k
+
+
+# ------------------------------------------------------------------------------------------
+#  Logging                         (reference: parla/comps/determiter/logging.py:4-94)
+# ------------------------------------------------------------------------------------------
+
+@dataclass
+class SketchAndPrecondLog:
+    time_sketch: float = 0.0
+    time_factor: float = 0.0
+    time_presolve: float = 0.0
+    time_convert: float = 0.0
+    time_iterate: float = 0.0
+    times: np.ndarray | None = None
+    errors: np.ndarray | None = None
+    error_desc: str = "Fill in."
+
+    @property
+    def time_setup(self):
+        # logging.py:63-70
+        return self.time_sketch + self.time_factor + self.time_convert
+
+    def wrap_up(self, iter_errors, init_error):
+        # logging.py:72-94: amortised per-iteration clock, errors[0] = error at x = 0.
+        iter_errors = np.atleast_1d(np.asarray(iter_errors, dtype=float))
+        t0 = self.time_setup
+        ramp = np.linspace(0.0, self.time_iterate, iter_errors.size, endpoint=True)
+        self.times = np.concatenate(([t0], t0 + self.time_presolve + ramp))
+        self.errors = np.concatenate(([init_error], iter_errors))
+
+
+# ------------------------------------------------------------------------------------------
+#  Preconditioned operator         (reference: parla/comps/preconditioning.py:16-79)
+# ------------------------------------------------------------------------------------------
+
+def svd_right_precond(A_ske):
+    """preconditioning.py:70-79.  M = V / sigma restricted to the numerical rank."""
+    U, sig, Vh = sla.svd(A_ske, full_matrices=False, check_finite=False)
+    rank = int(np.count_nonzero(sig > sig[0] * A_ske.shape[1] * EPS))
+    U, sig, Vh = U[:, :rank], sig[:rank], Vh[:rank, :]
+    return Vh.T / sig, U, sig, Vh
+
+
+class LiftedPrecondOperator:
+    """[A; sqrt(delta) I] composed with a right preconditioner.  preconditioning.py:16-67.
+
+    upper_tri=True : M = R^{-1} (triangular solves, :26-41)
+    upper_tri=False: M = R      (dense products, :45-57)
+    The reference materialises the lifted matrix (:6-13); here the identity block is applied
+    implicitly, which is the same linear map.
+    """
+
+    def __init__(self, A, delta, R, upper_tri):
+        self.A = A
+        self.m, self.n = A.shape
+        self.sd = math.sqrt(delta)
+        self.R = R
+        self.tri = bool(upper_tri)
+        self.shape = (self.m + (self.n if delta > 0 else 0), R.shape[1])
+
+    def precond(self, z):            # M_fwd, :40/:56
+        if self.tri:
+            return sla.solve_triangular(self.R, z, lower=False, check_finite=False)
+        return self.R @ z
+
+    def precond_t(self, w):          # M_adj, :41/:57
+        if self.tri:
+            return sla.solve_triangular(self.R, w, trans='T', lower=False, check_finite=False)
+        return self.R.T @ w
+
+    def matvec(self, z):             # forward(), :26-31 / :45-48
+        x = self.precond(z)
+        top = self.A @ x
+        return top if self.sd == 0 else np.concatenate((top, self.sd * x))
+
+    def rmatvec(self, u):            # adjoint(), :33-38 / :50-54
+        w = self.A.T @ u[:self.m]
+        if self.sd > 0:
+            w = w + self.sd * u[self.m:]
+        return self.precond_t(w)
+
+
+# ------------------------------------------------------------------------------------------
+#  LSQR                            (reference: parla/comps/determiter/lsqr.py:63-574)
+# ------------------------------------------------------------------------------------------
+
+def sym_ortho(a, b):
+    """Stable Givens rotation, lsqr.py:63-95.  Returns (c, s, r)."""
+    if b == 0:
+        return np.sign(a), 0.0, abs(a)
+    if a == 0:
+        return 0.0, np.sign(b), abs(b)
+    if abs(b) > abs(a):
+        t = a / b
+        s = np.sign(b) / math.sqrt(1.0 + t * t)
+        return s * t, s, b / s
+    t = b / a
+    c = np.sign(a) / math.sqrt(1.0 + t * t)
+    return c, c * t, a / c
+
+
+@dataclass
+class LsqrResult:
+    x: np.ndarray
+    istop: int
+    itn: int
+    r1norm: float
+    r2norm: float
+    anorm: float
+    acond: float
+    arnorms: np.ndarray      # history; a 0-d value on the early-exit path (lsqr.py:392-395)
+    xnorm: float
+
+
+def lsqr(op, b, atol, btol, iter_lim, conlim=1e8, x0=None):
+    """Paige-Saunders LSQR with PARLA's modifications (damp = 0 always on this path).
+
+    lsqr.py:98-574.  Differences of the reference from SciPy that matter and are kept:
+      * arnorm history: arnorms[itn] is recorded BEFORE step itn+1 (:413), trimmed at :572;
+      * x0 is used directly: x = x0, u = b - A x0 (:367-370);
+      * early exit when alfa*beta == 0 returns the scalar arnorm (:392-395).
+    Stopping rules :500-526 (istop 1..7).
+    """
+    b = np.asarray(b, dtype=float).reshape(-1)
+    n = op.shape[1]
+    ctol = 1.0 / conlim if conlim > 0 else 0.0
+    anorm = acond = ddnorm = xnorm = xxnorm = z = 0.0
+    cs2, sn2 = -1.0, 0.0
+    bnorm = float(np.linalg.norm(b))
+    if x0 is None:
+        x = np.zeros(n)
+        u = b.copy()
+        beta = bnorm
+    else:
+        x = np.array(x0, dtype=float)
+        u = b - op.matvec(x)
+        beta = float(np.linalg.norm(u))
+    if beta > 0:
+        u = u / beta
+        v = op.rmatvec(u)
+        alfa = float(np.linalg.norm(v))
+    else:
+        v = x.copy()
+        alfa = 0.0
+    if alfa > 0:
+        v = v / alfa
+    w = v.copy()
+    rhobar, phibar = alfa, beta
+    rnorm = beta
+    arnorm = alfa * beta
+    if arnorm == 0:
+        return LsqrResult(x, 0, 0, rnorm, rnorm, anorm, acond, np.float64(arnorm), xnorm)
+
+    hist = -np.ones(iter_lim)
+    itn, istop = 0, 0
+    while itn < iter_lim:
+        hist[itn] = arnorm
+        itn += 1
+        # bidiagonalisation step (:421-430)
+        u = op.matvec(v) - alfa * u
+        beta = float(np.linalg.norm(u))
+        if beta > 0:
+            u = u / beta
+            anorm = math.sqrt(anorm * anorm + alfa * alfa + beta * beta)
+            v = op.rmatvec(u) - beta * v
+            alfa = float(np.linalg.norm(v))
+            if alfa > 0:
+                v = v / alfa
+        # damp == 0  =>  rhobar1 = rhobar, psi = 0 (:434-438)
+        cs, sn, rho = sym_ortho(rhobar, beta)
+        theta = sn * alfa
+        rhobar = -cs * alfa
+        phi = cs * phibar
+        phibar = sn * phibar
+        tau = sn * phi
+        # solution / search-direction update (:449-457)
+        dk_sq = float(np.dot(w, w)) / (rho * rho)
+        x = x + (phi / rho) * w
+        w = v + (-theta / rho) * w
+        ddnorm += dk_sq
+        # norm(x) estimate via a second rotation (:462-471)
+        delta_ = sn2 * rho
+        gambar = -cs2 * rho
+        rhs = phi - delta_ * z
+        zbar = rhs / gambar
+        xnorm = math.sqrt(xxnorm + zbar * zbar)
+        gamma = math.sqrt(gambar * gambar + theta * theta)
+        cs2, sn2 = gambar / gamma, theta / gamma
+        z = rhs / gamma
+        xxnorm += z * z
+        # convergence estimates (:476-498)
+        acond = anorm * math.sqrt(ddnorm)
+        rnorm = math.sqrt(phibar * phibar)
+        arnorm = alfa * abs(tau)
+        test1 = rnorm / bnorm
+        test2 = arnorm / (anorm * rnorm + EPS)
+        test3 = 1.0 / (acond + EPS)
+        t1 = test1 / (1.0 + anorm * xnorm / bnorm)
+        rtol = btol + atol * anorm * xnorm / bnorm
+        # stopping rules, later assignments win (:504-526)
+        if itn >= iter_lim:
+            istop = 7
+        if 1 + test3 <= 1:
+            istop = 6
+        if 1 + test2 <= 1:
+            istop = 5
+        if 1 + t1 <= 1:
+            istop = 4
+        if test3 <= ctol:
+            istop = 3
+        if test2 <= atol:
+            istop = 2
+        if test1 <= rtol:
+            istop = 1
+        if istop:
+            break
+    return LsqrResult(x, istop, itn, rnorm, rnorm, anorm, acond, hist[hist > -1], xnorm)
+
+
+# ------------------------------------------------------------------------------------------
+#  PcSS2 + SPO / SSO1              (reference: determiter/saddle.py:180-217, drivers/least_squares.py)
+# ------------------------------------------------------------------------------------------
+
+def pcss2_overdetermined(A, b, delta, tol, iter_lim, R, upper_tri, z0):
+    """Over-determined branch of PcSS2.__call__, saddle.py:187-201.  Returns (x, y, arnorms)."""
+    m, n = A.shape
+    op = LiftedPrecondOperator(A, delta, R, upper_tri)
+    rhs = np.concatenate((b, np.zeros(n))) if delta > 0 else b
+    res = lsqr(op, rhs, atol=tol, btol=tol, iter_lim=iter_lim, x0=z0)
+    x = op.precond(res.x)
+    y = rhs[:m] - A @ x
+    return x, y, res.arnorms
+
+
+def dim_checks(sampling_factor, n_rows, n_cols):
+    """least_squares.py:89-104."""
+    assert n_rows >= n_cols
+    d = int(sampling_factor * n_cols)
+    if d > n_rows:
+        warnings.warn(f"embedding dimension d={d} exceeds the {n_rows} rows of the data matrix; "
+                      f"proceeding with d={n_rows} (very inefficient).")
+        d = n_rows
+    assert d >= n_cols
+    return d
+
+
+class SPO:
+    """Sketch-and-precondition least squares, least_squares.py:206-369 (mode qr/chol/svd).
+
+    "SAP1" == mode 'qr', "SAP2" == mode 'svd' (SURVEY.md section 0).
+    """
+
+    def __init__(self, sketch_op_gen, sampling_factor, mode='qr'):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+        self.mode = mode
+
+    def __call__(self, A, b, delta, tol, iter_lim, rng, logging=True):
+        m, n = A.shape
+        sd = math.sqrt(delta)
+        d = dim_checks(self.sampling_factor, m, n)
+        rng = np.random.default_rng(rng)
+        clock = time.time if logging else (lambda: 0.0)
+        log = SketchAndPrecondLog()
+
+        t = clock()
+        S = self.sketch_op_gen(d, m, rng)                       # :302
+        A_ske = S @ A                                           # :303
+        log.time_sketch = clock() - t
+
+        t = clock()
+        if self.mode == 'qr':                                   # :306-316
+            if delta > 0:
+                A_ske = np.vstack((A_ske, sd * np.eye(n)))
+            Q, R = sla.qr(A_ske, mode='economic')
+            log.time_factor = clock() - t
+            t = clock()
+            b_ske = S @ b
+            z_ske = Q[:d].T @ b_ske
+            x_ske = sla.solve_triangular(R, z_ske, lower=False)
+        elif self.mode == 'chol':                               # :317-329
+            G = A_ske.T @ A_ske + delta * np.eye(n)
+            R = sla.cholesky(G, lower=False, check_finite=False)
+            log.time_factor = clock() - t
+            t = clock()
+            b_ske = S @ b
+            z_ske = sla.solve_triangular(R, A_ske.T @ b_ske, lower=False, trans='T')
+            x_ske = sla.solve_triangular(R, z_ske, lower=False)
+        elif self.mode == 'svd':                                # :330-339
+            if delta > 0:
+                A_ske = np.vstack((A_ske, sd * np.eye(n)))
+            R, U, _sig, _Vh = svd_right_precond(A_ske)
+            log.time_factor = clock() - t
+            t = clock()
+            b_ske = S @ b
+            z_ske = U[:d].T @ b_ske
+            x_ske = R @ z_ske
+        else:
+            raise ValueError()                                  # :341
+
+        # presolve acceptance test (:344-352)
+        r = A @ x_ske - b
+        if delta > 0:
+            r = np.concatenate((r, sd * x_ske))
+        rel_err = np.linalg.norm(r) / np.linalg.norm(b)
+        if rel_err >= 1 or (rel_err > 1e-15 and R.shape[0] != R.shape[1]):
+            z_ske = None
+        log.time_presolve = clock() - t
+
+        t = clock()
+        tri = self.mode in ('qr', 'chol')
+        x, y, arnorms = pcss2_overdetermined(A, b, delta, tol, iter_lim, R, tri, z_ske)   # :356-357
+        log.time_iterate = clock() - t
+
+        if logging:                                             # :360-367
+            g = A.T @ b
+            g = sla.solve_triangular(R, g, trans='T', lower=False) if tri else R.T @ g
+            log.wrap_up(arnorms, float(np.linalg.norm(g)))
+            log.error_desc = "2-norm of the residual of the preconditioned normal equations"
+        self.last_y = y
+        return x, log
+
+
+class SSO1:
+    """Sketch-and-solve, least_squares.py:114-189."""
+
+    def __init__(self, sketch_op_gen, sampling_factor, lapack_driver=None, overwrite_sketch=True):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+        self.lapack_driver = lapack_driver
+
+    def __call__(self, A, b, delta, tol, iter_lim, rng, logging=True):
+        if not np.isnan(tol):
+            warnings.warn('SSO1 cannot control approximation error; "tol" is ignored.')
+        if iter_lim > 1:
+            warnings.warn('SSO1 is not iterative; "iter_lim" is ignored.')
+        m, n = A.shape
+        d = dim_checks(self.sampling_factor, m, n)
+        rng = np.random.default_rng(rng)
+        clock = time.time if logging else (lambda: 0.0)
+        t = clock()
+        S = self.sketch_op_gen(d, m, rng)
+        A_ske, b_ske = S @ A, S @ b
+        log = {'time_sketch': clock() - t}
+        t = clock()
+        if delta > 0:
+            A_ske = np.vstack((A_ske, math.sqrt(delta) * np.eye(n)))
+            b_ske = np.concatenate((b_ske, np.zeros(n)))
+        x = sla.lstsq(A_ske, b_ske, cond=None, check_finite=False,
+                      lapack_driver=self.lapack_driver)[0]
+        log['time_solve'] = clock() - t
+        return x, log
+
+
+# ------------------------------------------------------------------------------------------
+#  Low-rank path: orth / RS1 / RF1 / QB1 / QB2 / SVD1 / EVD1
+# ------------------------------------------------------------------------------------------
+
+def orth(S):
+    """utils/linalg_wrappers.py:6-7: Q factor of an economic Householder QR."""
+    return sla.qr(S, mode='economic')[0]
+
+
+class RS1:
+    """Power-iteration row sketcher, comps/sketchers/aware.py:118-184."""
+
+    def __init__(self, sketch_op_gen, num_pass, stabilizer, passes_per_stab):
+        self.sketch_op_gen = sketch_op_gen
+        self.num_pass = num_pass
+        self.stabilizer = stabilizer
+        self.passes_per_stab = passes_per_stab
+
+    def __call__(self, A, k, rng):
+        assert self.num_pass >= 0                               # :160
+        rng = np.random.default_rng(rng)
+        done = 0
+        if self.num_pass % 2 == 0:                              # :163-164
+            S = self.sketch_op_gen(A.shape[1], k, rng)
+        else:                                                   # :165-169
+            S = A.T @ self.sketch_op_gen(A.shape[0], k, rng)
+            done = 1
+            if self.passes_per_stab == 1:
+                S = self.stabilizer(S)
+        for _ in range((self.num_pass - done) // 2):            # :170-183
+            S = A @ S
+            done += 1
+            if done % self.passes_per_stab == 0:
+                S = self.stabilizer(S)
+            S = A.T @ S
+            done += 1
+            if done % self.passes_per_stab == 0:
+                S = self.stabilizer(S)
+        return S
+
+
+class RF1:
+    """Rangefinder, comps/rangefinders.py:126-188."""
+
+    def __init__(self, rso):
+        self.rso = rso
+
+    def __call__(self, A, k, tol, rng):
+        assert 0 < k <= min(A.shape)                            # :176-177
+        if not np.isnan(tol):
+            warnings.warn('RF1 cannot control approximation error; "tol" is ignored.')
+        rng = np.random.default_rng(rng)
+        S = self.rso(A, k, rng)
+        return sla.qr(A @ S, mode='economic')[0]                # :186-187
+
+
+class QB1:
+    """comps/qb.py:286-352."""
+
+    def __init__(self, rf):
+        self.rangefinder = rf
+
+    def __call__(self, A, k, tol, rng):
+        assert 0 < k <= min(A.shape)
+        if not np.isnan(tol):
+            assert 0 <= tol < 1
+        rng = np.random.default_rng(rng)
+        Q = self.rangefinder(A, k, tol, rng)
+        return Q, Q.T @ A
+
+
+class QB2:
+    """Blocked, tolerance-controlled QB with in-place deflation, comps/qb.py:355-482."""
+
+    def __init__(self, rf, blk, overwrite_a):
+        self.rangefinder = rf
+        self.blk = blk
+        self.overwrite_a = overwrite_a
+
+    def __call__(self, A, k, tol, rng):
+        if not self.overwrite_a:                                # :442-443
+            A = np.array(A, copy=True)
+        assert k > 0
+        lim = min(A.shape)
+        if k > lim:                                             # :445-452
+            warnings.warn(f"target rank k={k} exceeds min{A.shape}; using k={lim}.")
+            k = lim
+        use_tol = (not np.isnan(tol)) and tol > 0               # :454
+        if use_tol:
+            sq_norm = np.linalg.norm(A, 'fro') ** 2
+            stop_at = sq_norm * tol ** 2
+        rng = np.random.default_rng(rng)
+        m, n = A.shape
+        Q = np.empty((m, 0))
+        B = np.empty((0, n))
+        blk = self.blk
+        while True:                                             # :463-481
+            if B.shape[0] + blk > k:
+                blk = k - B.shape[0]
+            Qi = self.rangefinder(A, blk, np.nan, rng)
+            Qi = Qi - Q @ (Q.T @ Qi)                            # project_out, :603-613
+            Qi = sla.qr(Qi, mode='economic')[0]
+            Bi = Qi.T @ A
+            Q = np.column_stack((Q, Qi))
+            B = np.vstack((B, Bi))
+            A -= Qi @ Bi
+            if use_tol:
+                sq_norm -= np.linalg.norm(Bi, 'fro') ** 2
+                if sq_norm <= stop_at:
+                    break
+            if B.shape[0] >= k:
+                break
+        return Q, B
+
+
+class SVD1:
+    """drivers/svd.py:126-176."""
+
+    def __init__(self, qb):
+        self.qb = qb
+
+    def __call__(self, A, k, tol, over, rng):
+        rng = np.random.default_rng(rng)
+        Q, B = self.qb(A, k + over, tol, rng)
+        U, s, Vh = sla.svd(B, full_matrices=False)
+        if over > 0:                                            # :165-169
+            c = min(k, s.size)
+            U, s, Vh = U[:, :c], s[:c], Vh[:c]
+        keep = ~(s < 10 * EPS)                                  # :170-174
+        if not np.all(keep):
+            U, s, Vh = U[:, keep], s[keep], Vh[keep]
+        return Q @ U, s, Vh
+
+
+class EVD1:
+    """drivers/evd.py:211-289 (A symmetric)."""
+
+    def __init__(self, qb):
+        self.qb = qb
+
+    def __call__(self, A, k, tol, over, rng):
+        assert 0 < k <= min(A.shape)
+        if not np.isnan(tol):
+            assert 0 <= tol < np.inf
+        rng = np.random.default_rng(rng)
+        Q, B = self.qb(A, k + over, tol / 2, rng)               # :276
+        lamb, U = sla.eigh(B @ Q)                               # :278-279
+        mag = np.abs(lamb)
+        r = min(k, Q.shape[1], int(np.count_nonzero(mag > 10 * EPS)))
+        order = np.argsort(-mag)[:r]                            # :284
+        return Q @ U[:, order], lamb[order]
+
+
+# ------------------------------------------------------------------------------------------
+#  Synthetic matrices used by the reference tests (parla/tests/matmakers.py:7-41)
+# ------------------------------------------------------------------------------------------
+
+def orthonormal_operator(n_rows, n_cols, rng):
+    """utils/sketching.py:9-17 (sign-normalised Q of a Gaussian matrix)."""
+    if n_rows < n_cols:
+        return orthonormal_operator(n_cols, n_rows, rng).T
+    rng = np.random.default_rng(rng)
+    G = gaussian_operator(n_rows, n_cols, rng)
+    Q, R = sla.qr(G, mode='economic')
+    return Q * np.sign(np.diag(R))
+
+
+def rand_low_rank(n_rows, n_cols, spectrum, rng, factors=False):
+    """tests/matmakers.py:7-21."""
+    rng = np.random.default_rng(rng)
+    if isinstance(spectrum, int):
+        spectrum = rng.random(size=(spectrum,))
+    spectrum = np.sort(spectrum)[::-1]
+    spectrum = spectrum / spectrum[0]
+    rank = spectrum.size
+    U = orthonormal_operator(n_rows, rank, rng)
+    V = orthonormal_operator(rank, n_cols, rng)
+    M = (U * spectrum) @ V
+    return (M, U, spectrum, V) if factors else M
+
+
+def exponent_spectrum(n_rows, n_cols, rank, rng, spectrum_param, factors=False):
+    """tests/matmakers.py:34-36."""
+    spec = np.exp((-np.arange(1, rank) + 1) / spectrum_param)
+    return rand_low_rank(n_rows, n_cols, spec, rng, factors)
