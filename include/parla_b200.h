@@ -1,0 +1,177 @@
+/* libparla_b200 -- C ABI of the B200 (sm_100a) kernels behind PARLA's randomized-sketching hot path.
+ *
+ * Conventions
+ *   - Every matrix is ROW-MAJOR (numpy C order) fp64; `ld*` are leading dimensions in ELEMENTS.
+ *   - All data pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on it (no hidden
+ *     device synchronisation) unless stated otherwise.
+ *   - Return value: 0 = ok, <0 = -(index of the offending argument, 1-based), >0 = cudaError_t.
+ *     pla_last_error() returns a thread-local description.  Nothing throws or exits.
+ *   - The library never allocates device memory: scratch comes in through `ws` / `ws_bytes`
+ *     (query the matching *_workspace_bytes()).
+ *   - `istop_dev` (may be NULL): device int; when non-NULL and *istop_dev != 0 the call is a no-op.
+ *     This lets a host loop enqueue LSQR iterations ahead of the convergence test.
+ *
+ * Each entry point names the reference call site (BallisticLA/parla v0.1.4, file:line) it replaces.
+ */
+#ifndef PARLA_B200_H
+#define PARLA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int pla_version(void);
+const char* pla_last_error(void);
+int pla_num_sms(void);
+
+/* ---------------------------------------------------------------- K4: streaming GEMV pass
+ * Replaces  parla/comps/preconditioning.py:30  `out = A_lift @ work`            (DOT)
+ *           parla/comps/preconditioning.py:34  `np.dot(A.T, arg[:m], out=work)` (AXPY)
+ *           parla/drivers/least_squares.py:344 `r = A @ x_ske - b`, :361 `ar0 = A.T @ b`
+ *           parla/comps/determiter/saddle.py:199 `y = b[:m] - A @ x`
+ * in ONE read of A:
+ *     DOT :  u_i <- sa * (A[i,:] . w) + su * u_i            (u updated in place)
+ *     AXPY:  z   <- sum_i A[i,:]^T q_i,  q = g if AXPY_G else (new) u
+ *     zss[0..n) = z (zeros without AXPY),  zss[n] = sum_i u_i^2  (new u; 0 if u == NULL)
+ * sa/su come from sc_dev[0], sc_dev[1] when sc_dev != NULL (device scalars), else the immediates.
+ * 1 <= n <= PLA_PASS_MAX_N (odd n: <= 4096).                                                       */
+#define PLA_PASS_DOT 1
+#define PLA_PASS_AXPY 2
+#define PLA_PASS_AXPY_G 4
+#define PLA_PASS_MAX_N 8192
+size_t pla_stream_pass_workspace_bytes(int64_t m, int64_t n);
+int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
+                        const double* g, const double* sc_dev, double sa, double su, double* zss, int flags,
+                        const int* istop_dev, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K3b: triangular solve, one rhs
+ * Replaces scipy.linalg.solve_triangular(R, x, trans, lower=False) at
+ *   parla/comps/preconditioning.py:28,37,40,41 and parla/drivers/least_squares.py:316,363.
+ * R is n x n upper triangular (strict lower part ignored).  trans = 0: R x = b;  1: R^T x = b.
+ * x may alias b.                                                                                  */
+int pla_trsv_upper_f64(const double* R, int64_t n, int64_t ldr, int trans, const double* b, double* x,
+                       const int* istop_dev, void* stream);
+
+/* ---------------------------------------------------------------- LSQR recurrences on device
+ * Replaces the scalar/vector part of parla/comps/determiter/lsqr.py:342-395 (init) and :412-526
+ * (one iteration) so that the host never synchronises inside the loop.
+ * State layout: dstate = PLA_LSQR_NDOUBLE doubles, istate = PLA_LSQR_NINT ints (see lsqr_step.cu).
+ *   t   : M^T (A^T u~)   (preconditioned adjoint product of the UNNORMALISED u~ from the pass)
+ *   zss : output of pla_stream_pass_f64 (only zss[n] = |u~|^2 is read here)
+ *   bsq_dev : device scalar |b|^2 (pla_sumsq_f64);  x0 : initial iterate in preconditioned
+ *             coordinates or NULL (lsqr.py:363-370)
+ * After the call dstate[PLA_LSQR_SA..SU] hold the (sa, su) of the next pass.                      */
+#define PLA_LSQR_NDOUBLE 32
+#define PLA_LSQR_NINT 8
+#define PLA_LSQR_ALFA 0
+#define PLA_LSQR_BETA 1
+#define PLA_LSQR_RHOBAR 2
+#define PLA_LSQR_PHIBAR 3
+#define PLA_LSQR_ANORM 4
+#define PLA_LSQR_DDNORM 5
+#define PLA_LSQR_XXNORM 6
+#define PLA_LSQR_Z 7
+#define PLA_LSQR_CS2 8
+#define PLA_LSQR_SN2 9
+#define PLA_LSQR_BNORM 10
+#define PLA_LSQR_ARNORM 11
+#define PLA_LSQR_XNORM 12
+#define PLA_LSQR_ACOND 13
+#define PLA_LSQR_RNORM 14
+#define PLA_LSQR_SA 15
+#define PLA_LSQR_SU 16
+#define PLA_LSQR_ATOL 17
+#define PLA_LSQR_BTOL 18
+#define PLA_LSQR_CTOL 19
+#define PLA_LSQR_ISTOP 0   /* istate: 0 running, 1..7 as lsqr.py:500-526, 100 = alfa*beta == 0 at init */
+#define PLA_LSQR_ITN 1
+#define PLA_LSQR_ITERLIM 2
+int pla_lsqr_init_f64(int64_t n, const double* t, const double* zss, const double* bsq_dev, double atol,
+                      double btol, double conlim, int iter_lim, const double* x0, double* x, double* v,
+                      double* w, double* dstate, int* istate, void* stream);
+int pla_lsqr_step_f64(int64_t n, const double* t, const double* zss, double* x, double* v, double* w,
+                      double* dstate, int* istate, double* arnorm_hist, void* stream);
+/* ridge (delta > 0) rows of [A; sqrt(delta) I], applied implicitly (the reference materialises
+ * them: parla/comps/preconditioning.py:6-13,35-36):
+ *   ub <- sa * sd * xw + su * ub ;  zss[0..n) += sd * ub ;  zss[n] += |ub|^2                      */
+int pla_lsqr_ridge_f64(int64_t n, double sd, const double* xw, double* ub, const double* sc_dev, double sa,
+                       double su, double* zss, const int* istop_dev, void* stream);
+
+/* ---------------------------------------------------------------- K2: SJLT sketch
+ * Replaces `S @ A` for the scipy CSC operator of parla/utils/sketching.py:51-74 applied at
+ * parla/drivers/least_squares.py:303,314 (scipy.sparse csc_matvecs).
+ * S is d x m with exactly k nonzeros per column, values sign/sqrt(k).
+ *   pla_sjlt_plan_f64: builds the destination-major (CSR) plan from the index form
+ *       rows[m*k] (int32, row index of the q-th nonzero of column i at rows[i*k+q]),
+ *       signs[m*k] (int8, +1/-1).  plan: d+1 offsets (int64) followed by m*k packed entries (int32:
+ *       source row * 2 + (sign < 0)), within each destination ordered by source row (deterministic).
+ *   pla_sjlt_apply_f64: out[d x n] (+)= scale * S @ A,  accumulate = 0 overwrites; when bvec != NULL
+ *       also out_b[r * ldob] (+)= scale * (S @ bvec)[r] (the `S @ b` of least_squares.py:314) in the same launch.
+ *   Segments longer than 8192 entries per destination row are left in arrival order (the sum is then
+ *   correct but its rounding is not run-to-run reproducible).                                      */
+size_t pla_sjlt_plan_bytes(int64_t d, int64_t m, int64_t k);
+size_t pla_sjlt_plan_workspace_bytes(int64_t d, int64_t m, int64_t k);
+int pla_sjlt_plan_f64(const int32_t* rows, const int8_t* signs, int64_t m, int64_t k, int64_t d, void* plan,
+                      void* ws, size_t ws_bytes, void* stream);
+int pla_sjlt_apply_f64(const void* plan, int64_t d, int64_t m, int64_t k, const double* A, int64_t n,
+                       int64_t lda, const double* bvec, double scale, double* out, int64_t ldo, double* out_b,
+                       int64_t ldob, int accumulate, void* stream);
+/* Validation hook (SYNCHRONISES): number of out-of-range row indices seen while planning.          */
+int pla_sjlt_plan_status(const void* plan, int64_t* bad_index_count_host);
+/* Native (throughput) operator: index form generated on device from Philox4x32-10; column i of S
+ * depends only on (seed, col_offset + i), so row-sharded ranks generate consistent slices.         */
+int pla_sjlt_generate(int64_t d, int64_t m, int64_t k, uint64_t seed, int64_t col_offset, int32_t* rows,
+                      int8_t* signs, void* stream);
+
+/* ---------------------------------------------------------------- FP64 tensor-core GEMM (DMMA)
+ * C[M x N] = alpha * op(A) * op(B) + beta * C, op(X) = X or X^T (transa/transb = 0/1).
+ * Replaces the OpenBLAS dgemm behind `S @ A` (dense S; least_squares.py:303), `A @ S`, `A.T @ S`
+ * (sketchers/aware.py:166,175,179), `Y = A @ S` (rangefinders.py:186), `B = Q.T @ A` (qb.py:351,471),
+ * `A -= Qi @ Bi` (qb.py:475), project_out (qb.py:612), `U = Q @ U` (svd.py:175), `C = B @ Q`,
+ * `V = Q @ U` (evd.py:278,288).  Split-K partials are reduced in a fixed order (deterministic).    */
+size_t pla_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int pla_gemm_f64(int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                 int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* ws,
+                 size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- K1: Gaussian sketch, S never in HBM
+ * Replaces `S = rng.normal(0, 1/sqrt(d), (d, m))` (parla/utils/sketching.py:23-24) followed by
+ * `A_ske = S @ A` (least_squares.py:303):  out[d x n] = beta*out + scale * G(seed)[0:d, off:off+m] @ A
+ * where G is the virtual Philox4x32-10 / Box-Muller operator defined in oracle/philox_ref.py.
+ * When bvec != NULL the rhs is sketched in the same launch: out[:, n] = beta*out[:, n] + scale * G @ bvec
+ * (`b_ske = S @ b`, least_squares.py:314), so out must have n+1 columns (ldo >= n+1).
+ * pla_philox_normal_fill_f64 materialises the same operator (test hook / small dense operators).  */
+size_t pla_sketch_gauss_workspace_bytes(int64_t d, int64_t n, int64_t m);
+int pla_sketch_gauss_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* bvec, int64_t d,
+                         uint64_t seed, int64_t col_offset, double scale, double beta, double* out, int64_t ldo,
+                         void* ws, size_t ws_bytes, void* stream);
+int pla_philox_normal_fill_f64(double* out, int64_t rows, int64_t cols, int64_t ldo, uint64_t seed,
+                               int64_t row_offset, int64_t col_offset, double scale, void* stream);
+
+/* ---------------------------------------------------------------- K3a/K6: Householder QR
+ * Replaces scipy.linalg.qr(A_ske, mode='economic') (least_squares.py:311; LAPACK dgeqrf+dorgqr),
+ * utils/linalg_wrappers.py:6-7 (orth), rangefinders.py:187, qb.py:470.
+ *   pla_geqrf_f64: in-place blocked Householder QR of the leading `ncols_factor` columns of the
+ *       M x N matrix A; the reflectors are applied to ALL N columns (append rhs columns to get
+ *       Q^T b for free).  On exit R is in the upper triangle, the reflector vectors below the
+ *       diagonal (unit diagonal implied, LAPACK layout), tau[ncols_factor].
+ *   pla_orgqr_f64: Q[M x K] (K = ncols_factor) with orthonormal columns from (A, tau).
+ * The panel kernel is a cooperative launch (grid barrier): grid <= number of SMs.                 */
+size_t pla_qr_workspace_bytes(int64_t M, int64_t N);
+int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64_t ncols_factor, double* tau, void* ws,
+                  size_t ws_bytes, void* stream);
+int pla_orgqr_f64(const double* A, int64_t M, int64_t K, int64_t lda, const double* tau, double* Q, int64_t ldq,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- small vector helpers
+ * out[0] = sum x_i^2 (deterministic two-stage).  Used for |b| (least_squares.py:347).             */
+int pla_sumsq_f64(const double* x, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream);
+size_t pla_sumsq_workspace_bytes(int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARLA_B200_H */

@@ -68,3 +68,45 @@ def gaussian_block(seed, row0, n_rows, col0, n_cols, scale=1.0):
         out[rr] = g.reshape(-1)
     lo = col0 - 4 * q_lo
     return scale * out[:, lo:lo + n_cols]
+
+
+def sjlt_columns(d, m, k, seed, col_offset=0):
+    """Index form (rows[m,k] int32, signs[m,k] int8) of the native SJLT operator
+    (``pla_sjlt_generate`` / parla_b200/csrc/sjlt.cu):
+
+    for column gi = col_offset + i, Philox blocks with ctr = (gi_lo, gi_hi, call, 0x534A4C54) and
+    key = (seed_lo, seed_hi), call = 0, 1, ...; the words are consumed in order.  Word 0 holds the
+    sign bits (bit q set -> -1).  Row q is floor(word * d / 2^32), redrawn while it duplicates an
+    earlier row of the same column (no redraw when d < k).  Integer arithmetic only: bit-exact.
+    """
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    key = np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint32)
+    rows = np.empty((m, k), dtype=np.int32)
+    signs = np.empty((m, k), dtype=np.int8)
+    gi = np.arange(col_offset, col_offset + m, dtype=np.uint64)
+    ncalls = 4                                        # enough words for k <= 8 plus a few redraws
+    words = []
+    for call in range(ncalls):
+        ctr = np.zeros((m, 4), dtype=np.uint32)
+        ctr[:, 0] = (gi & MASK).astype(np.uint32)
+        ctr[:, 1] = (gi >> SHIFT).astype(np.uint32)
+        ctr[:, 2] = call
+        ctr[:, 3] = 0x534A4C54
+        words.append(philox4x32_10(ctr, key))
+    words = np.concatenate(words, axis=1).astype(np.uint64)     # (m, 4*ncalls)
+    for i in range(m):
+        wi = 1
+        sbits = int(words[i, 0])
+        picked = []
+        for q in range(k):
+            while True:
+                if wi >= words.shape[1]:
+                    raise RuntimeError("ran out of precomputed Philox words; raise ncalls")
+                cand = int((int(words[i, wi]) * d) >> 32)
+                wi += 1
+                if d < k or cand not in picked:
+                    break
+            picked.append(cand)
+            rows[i, q] = cand
+            signs[i, q] = -1 if (sbits >> q) & 1 else 1
+    return rows, signs

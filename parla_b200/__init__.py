@@ -1,0 +1,18 @@
+"""parla_b200 -- B200-native implementation of PARLA's randomized-sketching hot path.
+
+Package-level names follow parla/__init__.py:8-19 for the components on the path.
+"""
+__version__ = '0.1.0'
+
+from .utils.sketching import gaussian_operator, sjlt_operator, as_device_operator
+from .utils.linalg_wrappers import orth
+from .comps.sketchers.oblivious import SkOpGA, SkOpSJ, SketchOpGen
+from .comps.sketchers.aware import RS1, RowSketcher
+from .comps.qb import QB1, QB2, QBDecomposer
+from .comps.rangefinders import RF1, RangeFinder
+from .comps.determiter.logging import SketchAndPrecondLog
+from .comps.determiter.saddle import PcSS2, PrecondSaddleSolver
+from .drivers.least_squares import SPO, SSO1, OverLstsqSolver
+from .drivers.svd import SVD1, SVDecomposer
+from .drivers.evd import EVD1, EVDecomposer
+from .parallel import RowSharded

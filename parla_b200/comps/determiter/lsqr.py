@@ -1,0 +1,86 @@
+"""LSQR with every vector and scalar resident on the device.
+
+Mirrors parla/comps/determiter/lsqr.py:98-574 (Paige-Saunders LSQR as modified by PARLA: arnorm
+history :413/:572, direct use of x0 :367-370, early return :392-395, stopping rules :500-526).
+The host loop below only ENQUEUES work: per iteration one triangular solve, one fused pass over
+A, (an all-reduce when row-sharded,) one transposed solve and one recurrence kernel.  The
+convergence flag lives in device memory; kernels turn into no-ops once it is set, so the host
+polls it a couple of iterations late through pinned memory instead of synchronising every step.
+"""
+import numpy as np
+import torch
+
+from ... import kernels as K
+from ...parallel import allreduce_
+
+F64 = torch.float64
+POLL_LAG = 2      # iterations the host may run ahead of the device-side stopping test
+
+
+def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=False, calc_var=False,
+         x0=None, _warm=None):
+    """A: PrecondOperator; b: device vector (this rank's rows).  Returns the reference's 10-tuple
+    (x, istop, itn, r1norm, r2norm, anorm, acond, arnorms, xnorm, var); x is a device tensor."""
+    if damp != 0.0 or calc_var:
+        raise NotImplementedError("PARLA always calls lsqr with damp=0, calc_var=False")
+    n = A.shape[1]
+    dev = b.device
+    if iter_lim is None:
+        iter_lim = 2 * n
+    iter_lim = int(iter_lim)
+
+    x, v, w = (torch.empty(n, dtype=F64, device=dev) for _ in range(3))
+    xw = torch.empty(A.n, dtype=F64, device=dev)
+    t = torch.empty(n, dtype=F64, device=dev)
+    dstate = torch.zeros(K.LSQR_NDOUBLE, dtype=F64, device=dev)
+    istate = torch.zeros(K.LSQR_NINT, dtype=torch.int32, device=dev)
+    hist = torch.full((iter_lim,), -1.0, dtype=F64, device=dev)
+    bsq = allreduce_(K.sumsq(b), A.group)
+
+    if _warm is not None:                       # presolve already did  u = b - A_pc x0  (lsqr.py:367-370)
+        u, ub, zss = _warm["u"], _warm["ub"], _warm["zss"]
+        t.copy_(_warm["t"])
+    else:
+        u = b.clone()
+        ub = torch.zeros(A.n, dtype=F64, device=dev) if A.delta > 0 else None
+        zss = torch.empty(A.n + 1, dtype=F64, device=dev)
+        if x0 is None:
+            A.adjoint_pass(u, None, zss, t)     # u = b, beta = |b|, A^T b   (:363-366,:372-375)
+            A.atb = zss[:A.n].clone()
+        else:
+            A.bidiag_pass(x0, u, ub, zss, xw, t, sa=-1.0, su=1.0)
+    K.lsqr_init(t, zss, bsq, atol, btol, conlim, iter_lim, x0, x, v, w, dstate, istate)
+
+    sc = dstate[K.LSQR_SA:K.LSQR_SA + 2]
+    istop_dev = istate[0:1]
+    pinned = [torch.zeros(K.LSQR_NINT, dtype=torch.int32).pin_memory() for _ in range(POLL_LAG + 1)]
+    events = [torch.cuda.Event() for _ in range(POLL_LAG + 1)]
+
+    def post(slot):
+        pinned[slot].copy_(istate, non_blocking=True)
+        events[slot].record()
+
+    post(0)
+    events[0].synchronize()
+    launched = 0
+    if int(pinned[0][0]) == 0:
+        for it in range(iter_lim):
+            if it >= POLL_LAG:
+                slot = (it - POLL_LAG) % (POLL_LAG + 1)
+                events[slot].synchronize()
+                if int(pinned[slot][0]) != 0:
+                    break
+            A.bidiag_pass(v, u, ub, zss, xw, t, sc=sc, istop=istop_dev)
+            K.lsqr_step(t, zss, x, v, w, dstate, istate, hist)
+            launched += 1
+            post(it % (POLL_LAG + 1))
+    torch.cuda.current_stream().synchronize()
+    ds = dstate.cpu().numpy()
+    ist = istate.cpu().numpy()
+    istop, itn = int(ist[0]), int(ist[1])
+    A.passes -= max(0, launched - itn)          # run-ahead launches were device-side no-ops
+    var = np.zeros(n)
+    if istop == 100:                            # alfa*beta == 0: scalar arnorm, as the reference (:392-395)
+        return x, 0, 0, ds[14], ds[14], 0.0, 0.0, np.float64(ds[11]), 0.0, var
+    arn = hist[:itn].cpu().numpy()
+    return x, istop, itn, ds[14], ds[14], ds[4], ds[13], arn, ds[12], var

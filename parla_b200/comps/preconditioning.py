@@ -1,0 +1,106 @@
+"""Right-preconditioned, ridge-lifted operator on the device.
+
+Mirrors parla/comps/preconditioning.py:16-67 (``a_lift_precond``) and :70-79 (``svd_right_precond``).
+Differences from the reference, all behaviour-preserving:
+  * ``[A; sqrt(delta) I]`` is never materialised (the reference copies A, :6-13); the identity rows
+    are applied by pla_lsqr_ridge_f64 on n-vectors;
+  * forward and adjoint products of one LSQR iteration share ONE pass over A
+    (:func:`PrecondOperator.bidiag_pass`), see parla_b200/csrc/stream_pass.cu.
+"""
+import math
+
+import torch
+
+from .. import kernels as K
+from ..parallel import allreduce_, unwrap
+
+F64 = torch.float64
+
+
+class PrecondOperator:
+    """A_pc = [A; sqrt(delta) I] M with M = R^{-1} (upper_tri) or M = R (dense n x r)."""
+
+    def __init__(self, A, delta, R, upper_tri):
+        self.A, self.row_offset, self.group = unwrap(A)
+        if self.A.dim() != 2:
+            raise ValueError("A must be 2-D")
+        if self.A.stride(1) != 1 and self.A.shape[1] > 1:
+            self.A = self.A.contiguous()
+        self.m_local, self.n = self.A.shape
+        self.m = A.shape[0]
+        self.delta = float(delta)
+        self.sd = math.sqrt(self.delta)
+        self.R = R
+        self.tri = bool(upper_tri)
+        self.rank = R.shape[1]
+        self.shape = (self.m + (self.n if self.delta > 0 else 0), self.rank)
+        self.passes = 0
+        self.atb = None          # cache of A^T b when a pass happened to produce it
+
+    # ---- M and M^T on n-vectors (preconditioning.py:40-41 / :56-57)
+    def precond(self, z, out=None, istop=None):
+        if self.tri:
+            return K.trsv_upper(self.R, z, trans=False, out=out, istop=istop)
+        if out is None:
+            out = torch.zeros(self.n, dtype=F64, device=z.device)
+        K.stream_pass(self.R, w=z, u=out, sa=1.0, su=0.0, flags=K.PASS_DOT, istop=istop)
+        return out
+
+    def precond_t(self, w, out=None, istop=None):
+        if self.tri:
+            return K.trsv_upper(self.R, w, trans=True, out=out, istop=istop)
+        zss = K.stream_pass(self.R, u=w, flags=K.PASS_AXPY, istop=istop)
+        if out is None:
+            return zss[:self.rank]
+        out.copy_(zss[:self.rank])     # (after LSQR has stopped nothing downstream reads `out`)
+        return out
+
+    # ---- one Golub-Kahan half-step pair in a single read of A
+    def bidiag_pass(self, z, u, ub, zss, xw, t, sc=None, sa=1.0, su=0.0, istop=None):
+        """u~ <- sa * A_pc z + su * u~ (top part in ``u``, ridge part in ``ub``);
+        t <- M^T [A; sd I]^T u~ ;  zss[n] <- |u~|^2.   (preconditioning.py:26-38 forward + adjoint)"""
+        self.precond(z, out=xw, istop=istop)
+        K.stream_pass(self.A, w=xw, u=u, sc=sc, sa=sa, su=su, zss=zss, flags=K.PASS_DOT | K.PASS_AXPY, istop=istop)
+        self.passes += 1
+        allreduce_(zss, self.group)
+        if self.delta > 0:
+            K.lsqr_ridge(self.sd, xw, ub, zss, sc=sc, sa=sa, su=su, istop=istop)
+        self.precond_t(zss[:self.n], out=t, istop=istop)
+        return t
+
+    def adjoint_pass(self, u, ub, zss, t):
+        """t <- M^T (A^T u + sd * ub), zss[n] <- |[u; ub]|^2 (no forward product)."""
+        K.stream_pass(self.A, u=u, zss=zss, flags=K.PASS_AXPY)
+        self.passes += 1
+        allreduce_(zss, self.group)
+        if self.delta > 0 and ub is not None:
+            K.lsqr_ridge(self.sd, None, ub, zss, sa=0.0, su=1.0)
+        self.precond_t(zss[:self.n], out=t)
+        return t
+
+    def residual_and_atb(self, x, b):
+        """y = b - A x and A^T b in one pass (saddle.py:199 and least_squares.py:361 fused)."""
+        y = b.clone()
+        zss = K.stream_pass(self.A, w=x, u=y, g=b, sa=-1.0, su=1.0, flags=K.PASS_DOT | K.PASS_AXPY | K.PASS_AXPY_G)
+        self.passes += 1
+        allreduce_(zss, self.group)
+        self.atb = zss[:self.n].clone()
+        return y
+
+
+def a_lift_precond(A, delta, R, upper_tri=False, k=1):
+    """Signature of parla/comps/preconditioning.py:16.  Returns (A_precond, M_fwd, M_adj)."""
+    if k != 1:
+        raise NotImplementedError()
+    op = PrecondOperator(A, delta, R, upper_tri)
+    return op, op.precond, op.precond_t
+
+
+def svd_right_precond(A_ske):
+    """parla/comps/preconditioning.py:70-79.  The small dense SVD is cuSOLVER glue."""
+    U, sigma, Vh = torch.linalg.svd(A_ske.contiguous(), full_matrices=False)
+    eps = torch.finfo(F64).eps
+    rank = int(torch.count_nonzero(sigma > sigma[0] * A_ske.shape[1] * eps))
+    Vh, U, sigma = Vh[:rank, :], U[:, :rank], sigma[:rank]
+    M = (Vh.T / sigma).contiguous()
+    return M, U, sigma, Vh

@@ -1,0 +1,37 @@
+"""Data-oblivious sketching-operator generators (OO layer over utils.sketching).
+
+Mirrors parla/comps/sketchers/oblivious.py:25-55: ``SketchOpGen.__call__(n_rows, n_cols, rng)``.
+"""
+from ...utils import sketching as usk
+
+
+class SketchOpGen:
+
+    def __call__(self, n_rows, n_cols, rng):
+        raise NotImplementedError()
+
+    exec = __call__
+
+
+class SkOpGA(SketchOpGen):
+    """Gaussian operator generator (oblivious.py:38-45)."""
+
+    def __init__(self, normalize=True):
+        self.normalize = normalize
+
+    def __call__(self, n_rows, n_cols, rng):
+        return usk.gaussian_operator(n_rows, n_cols, rng, self.normalize)
+
+    exec = __call__
+
+
+class SkOpSJ(SketchOpGen):
+    """SJLT generator (oblivious.py:48-55)."""
+
+    def __init__(self, vec_nnz=8):
+        self.vec_nnz = vec_nnz
+
+    def __call__(self, n_rows, n_cols, rng):
+        return usk.sjlt_operator(n_rows, n_cols, rng, self.vec_nnz)
+
+    exec = __call__

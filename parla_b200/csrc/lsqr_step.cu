@@ -1,0 +1,240 @@
+// Device-resident LSQR recurrences (single CTA; n-sized vectors only).
+//
+// Follows the Golub-Kahan / Paige-Saunders recurrences as PARLA runs them
+// (parla/comps/determiter/lsqr.py:342-395 initialisation, :412-526 iteration, damp == 0).
+// The m-sized work (A v, A^T u, |u|) is done by pla_stream_pass_f64 on an UNNORMALISED u~:
+//   lsqr.py:421-425  u = A v - alfa u ; beta = |u| ; u /= beta      ->  pass with (sa, su) = (1, -alfa/beta_prev)
+//   lsqr.py:427      v = A^T u - beta v                             ->  t / beta - beta v   (linearity)
+// so the only quantities needed here are t = M^T A^T u~ and |u~|^2.
+#include "common.cuh"
+#include "../../include/parla_b200.h"
+
+namespace pla {
+
+constexpr int LS_THREADS = 1024;
+
+__device__ __forceinline__ double sgn(double a) { return (a > 0.0) - (a < 0.0); }
+
+// lsqr.py:63-95
+__device__ __forceinline__ void sym_ortho(double a, double b, double& c, double& s, double& r) {
+    if (b == 0.0) { c = sgn(a); s = 0.0; r = fabs(a); }
+    else if (a == 0.0) { c = 0.0; s = sgn(b); r = fabs(b); }
+    else if (fabs(b) > fabs(a)) {
+        const double t = a / b;
+        s = sgn(b) / sqrt(1.0 + t * t);
+        c = s * t;
+        r = b / s;
+    } else {
+        const double t = b / a;
+        c = sgn(a) / sqrt(1.0 + t * t);
+        s = c * t;
+        r = a / c;
+    }
+}
+
+__global__ void __launch_bounds__(LS_THREADS) lsqr_init_kernel(long long n, const double* __restrict__ t,
+                                                               const double* __restrict__ zss,
+                                                               const double* __restrict__ bsq, double atol,
+                                                               double btol, double ctol, int iter_lim,
+                                                               const double* __restrict__ x0, double* x, double* v,
+                                                               double* w, double* ds, int* is) {
+    __shared__ double scratch[33];
+    const double beta = sqrt(zss[n]);
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) x[i] = x0 ? x0[i] : 0.0;
+    __syncthreads();
+    double alfa = 0.0;
+    if (beta > 0.0) {                                   // lsqr.py:372-375
+        double acc = 0.0;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const double vi = t[i] / beta;
+            v[i] = vi;
+            acc = fma(vi, vi, acc);
+        }
+        alfa = sqrt(block_sum(acc, scratch));
+    } else {                                            // lsqr.py:376-378
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) v[i] = x[i];
+    }
+    __syncthreads();
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        double vi = v[i];
+        if (alfa > 0.0) { vi = vi / alfa; v[i] = vi; }  // lsqr.py:380-381
+        w[i] = vi;                                      // :382
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < PLA_LSQR_NDOUBLE; ++i) ds[i] = 0.0;
+        ds[PLA_LSQR_ALFA] = alfa;
+        ds[PLA_LSQR_BETA] = beta;
+        ds[PLA_LSQR_RHOBAR] = alfa;
+        ds[PLA_LSQR_PHIBAR] = beta;
+        ds[PLA_LSQR_CS2] = -1.0;
+        ds[PLA_LSQR_BNORM] = sqrt(bsq[0]);
+        ds[PLA_LSQR_ARNORM] = alfa * beta;
+        ds[PLA_LSQR_RNORM] = beta;
+        ds[PLA_LSQR_SA] = 1.0;
+        ds[PLA_LSQR_SU] = beta > 0.0 ? -alfa / beta : 0.0;
+        ds[PLA_LSQR_ATOL] = atol;
+        ds[PLA_LSQR_BTOL] = btol;
+        ds[PLA_LSQR_CTOL] = ctol;
+        for (int i = 0; i < PLA_LSQR_NINT; ++i) is[i] = 0;
+        is[PLA_LSQR_ITERLIM] = iter_lim;
+        is[PLA_LSQR_ISTOP] = (alfa * beta == 0.0) ? 100 : 0;   // lsqr.py:392-395 early return
+    }
+}
+
+__global__ void __launch_bounds__(LS_THREADS) lsqr_step_kernel(long long n, const double* __restrict__ t,
+                                                               const double* __restrict__ zss, double* x, double* v,
+                                                               double* w, double* ds, int* is, double* hist) {
+    if (is[PLA_LSQR_ISTOP] != 0) return;
+    __shared__ double scratch[33];
+    const double eps = 2.220446049250313e-16;
+    // every thread snapshots the scalars it needs BEFORE the first barrier; thread 0 rewrites the
+    // state only after the last one.
+    double alfa = ds[PLA_LSQR_ALFA];
+    double anorm = ds[PLA_LSQR_ANORM];
+    const double rhobar0 = ds[PLA_LSQR_RHOBAR], phibar0 = ds[PLA_LSQR_PHIBAR];
+    const double beta = sqrt(zss[n]);                    // lsqr.py:422
+    const double alfa_prev = alfa;
+
+    // ---- v = A^T u - beta v ; alfa = |v| ; v /= alfa          (lsqr.py:424-430)
+    if (beta > 0.0) {
+        double acc = 0.0;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const double vi = t[i] / beta - beta * v[i];
+            v[i] = vi;
+            acc = fma(vi, vi, acc);
+        }
+        alfa = sqrt(block_sum(acc, scratch));
+        anorm = sqrt(anorm * anorm + alfa_prev * alfa_prev + beta * beta);
+    }
+    // ---- |w|^2 for ddnorm (lsqr.py:453-457) while w is still the old direction
+    double wacc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) wacc = fma(w[i], w[i], wacc);
+    const double ww = block_sum(wacc, scratch);
+
+    // ---- scalar recurrences, computed redundantly by every thread (identical results)
+    double cs, sn, rho;
+    sym_ortho(rhobar0, beta, cs, sn, rho);    // rhobar1 == rhobar (damp = 0)
+    const double theta = sn * alfa;
+    const double rhobar = -cs * alfa;
+    const double phi = cs * phibar0;
+    const double phibar = sn * phibar0;
+    const double tau = sn * phi;
+    const double t1 = phi / rho, t2 = -theta / rho;
+    const bool scale_v = (beta > 0.0) && (alfa > 0.0);
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        double vi = v[i];
+        if (scale_v) { vi = vi / alfa; v[i] = vi; }
+        const double wi = w[i];
+        x[i] = fma(t1, wi, x[i]);                          // :455
+        w[i] = fma(t2, wi, vi);                            // :456
+    }
+    if (threadIdx.x != 0) return;
+
+    const double ddnorm = ds[PLA_LSQR_DDNORM] + ww / (rho * rho);
+    const double cs2 = ds[PLA_LSQR_CS2], sn2 = ds[PLA_LSQR_SN2], zprev = ds[PLA_LSQR_Z];
+    double xxnorm = ds[PLA_LSQR_XXNORM];
+    const double delta = sn2 * rho;                        // :462-471
+    const double gambar = -cs2 * rho;
+    const double rhs = phi - delta * zprev;
+    const double zbar = rhs / gambar;
+    const double xnorm = sqrt(xxnorm + zbar * zbar);
+    const double gamma = sqrt(gambar * gambar + theta * theta);
+    const double z = rhs / gamma;
+    xxnorm += z * z;
+    const double acond = anorm * sqrt(ddnorm);             // :476-483
+    const double rnorm = sqrt(phibar * phibar);
+    const double arnorm = alfa * fabs(tau);
+    const double bnorm = ds[PLA_LSQR_BNORM];
+    const double atol = ds[PLA_LSQR_ATOL], btol = ds[PLA_LSQR_BTOL], ctol = ds[PLA_LSQR_CTOL];
+    const double test1 = rnorm / bnorm;                    // :500-526
+    const double test2 = arnorm / (anorm * rnorm + eps);
+    const double test3 = 1.0 / (acond + eps);
+    const double tt1 = test1 / (1.0 + anorm * xnorm / bnorm);
+    const double rtol = btol + atol * anorm * xnorm / bnorm;
+
+    const int itn_prev = is[PLA_LSQR_ITN];
+    hist[itn_prev] = ds[PLA_LSQR_ARNORM];                  // :413 (value BEFORE this step)
+    const int itn = itn_prev + 1;
+    int istop = 0;
+    if (itn >= is[PLA_LSQR_ITERLIM]) istop = 7;
+    if (1.0 + test3 <= 1.0) istop = 6;
+    if (1.0 + test2 <= 1.0) istop = 5;
+    if (1.0 + tt1 <= 1.0) istop = 4;
+    if (test3 <= ctol) istop = 3;
+    if (test2 <= atol) istop = 2;
+    if (test1 <= rtol) istop = 1;
+
+    ds[PLA_LSQR_ALFA] = alfa;
+    ds[PLA_LSQR_BETA] = beta;
+    ds[PLA_LSQR_RHOBAR] = rhobar;
+    ds[PLA_LSQR_PHIBAR] = phibar;
+    ds[PLA_LSQR_ANORM] = anorm;
+    ds[PLA_LSQR_DDNORM] = ddnorm;
+    ds[PLA_LSQR_XXNORM] = xxnorm;
+    ds[PLA_LSQR_Z] = z;
+    ds[PLA_LSQR_CS2] = gambar / gamma;
+    ds[PLA_LSQR_SN2] = theta / gamma;
+    ds[PLA_LSQR_ARNORM] = arnorm;
+    ds[PLA_LSQR_XNORM] = xnorm;
+    ds[PLA_LSQR_ACOND] = acond;
+    ds[PLA_LSQR_RNORM] = rnorm;
+    ds[PLA_LSQR_SA] = 1.0;
+    ds[PLA_LSQR_SU] = beta > 0.0 ? -alfa / beta : 0.0;
+    is[PLA_LSQR_ITN] = itn;
+    is[PLA_LSQR_ISTOP] = istop;
+}
+
+__global__ void __launch_bounds__(LS_THREADS) lsqr_ridge_kernel(long long n, double sd, const double* __restrict__ xw,
+                                                                double* ub, const double* sc, double sa, double su,
+                                                                double* zss, const int* istop) {
+    if (istop != nullptr && *istop != 0) return;
+    __shared__ double scratch[33];
+    if (sc != nullptr) { sa = sc[0]; su = sc[1]; }
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double xi = xw ? xw[i] : 0.0;
+        const double ui = fma(sa * sd, xi, su * ub[i]);
+        ub[i] = ui;
+        zss[i] = fma(sd, ui, zss[i]);
+        acc = fma(ui, ui, acc);
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) zss[n] += acc;
+}
+
+}  // namespace pla
+
+using namespace pla;
+
+extern "C" int pla_lsqr_init_f64(int64_t n, const double* t, const double* zss, const double* bsq_dev, double atol,
+                                 double btol, double conlim, int iter_lim, const double* x0, double* x, double* v,
+                                 double* w, double* dstate, int* istate, void* stream) {
+    PLA_CHECK_ARG(n >= 1, 1, "n < 1");
+    PLA_CHECK_ARG(t && zss && bsq_dev, 2, "null input");
+    PLA_CHECK_ARG(iter_lim >= 1, 8, "iter_lim < 1");
+    PLA_CHECK_ARG(x && v && w && dstate && istate, 10, "null state");
+    const double ctol = conlim > 0 ? 1.0 / conlim : 0.0;
+    lsqr_init_kernel<<<1, LS_THREADS, 0, (cudaStream_t)stream>>>(n, t, zss, bsq_dev, atol, btol, ctol, iter_lim, x0,
+                                                                  x, v, w, dstate, istate);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pla_lsqr_step_f64(int64_t n, const double* t, const double* zss, double* x, double* v, double* w,
+                                 double* dstate, int* istate, double* arnorm_hist, void* stream) {
+    PLA_CHECK_ARG(n >= 1, 1, "n < 1");
+    PLA_CHECK_ARG(t && zss, 2, "null input");
+    PLA_CHECK_ARG(x && v && w && dstate && istate && arnorm_hist, 4, "null state");
+    lsqr_step_kernel<<<1, LS_THREADS, 0, (cudaStream_t)stream>>>(n, t, zss, x, v, w, dstate, istate, arnorm_hist);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pla_lsqr_ridge_f64(int64_t n, double sd, const double* xw, double* ub, const double* sc_dev,
+                                  double sa, double su, double* zss, const int* istop_dev, void* stream) {
+    PLA_CHECK_ARG(n >= 1, 1, "n < 1");
+    PLA_CHECK_ARG(ub && zss, 4, "null vector");
+    lsqr_ridge_kernel<<<1, LS_THREADS, 0, (cudaStream_t)stream>>>(n, sd, xw, ub, sc_dev, sa, su, zss, istop_dev);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,453 @@
+// K3a / K6: blocked Householder QR of a row-major M x N matrix (LAPACK dgeqrf conventions) and
+// explicit formation of Q (dorgqr).
+//
+// Replaces scipy.linalg.qr(., mode='economic') on the hot path: the sketch factorisation
+// (parla/drivers/least_squares.py:311), the stabiliser `orth` (parla/utils/linalg_wrappers.py:6-7),
+// rangefinders.py:187 and qb.py:470.
+//
+// Panel (16 columns) factorisation: one cooperative kernel, rows distributed over the CTAs, ONE
+// grid barrier per column (the dot products needed by column j+1 are accumulated while column j's
+// reflector is applied).  Trailing matrix: W = V^T C (row-split partials, fixed-order reduction),
+// C -= V (T^T W) with T the compact-WY factor.  Every reduction has a fixed order => deterministic.
+#include "common.cuh"
+#include "../../include/parla_b200.h"
+
+namespace pla {
+
+constexpr int QR_NB = 16;
+constexpr int QR_THREADS = 256;
+constexpr int QR_NP = QR_NB + 1;         // partial sums per column step: sigma + 16 dots
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned int*)counter) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct PanelParams {
+    double* A; long long lda;
+    long long M;            // total rows
+    long long j0;           // first column (and first row) of the panel
+    int jb;                 // panel width (<= 16)
+    double* tau;            // tau + j0
+    double* gpart;          // [2][grid][QR_NP]
+    unsigned int* counter;  // zeroed before launch
+    long long rows_per_cta;
+};
+
+// Factor A[j0:M, j0:j0+jb] in place.
+__global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(const PanelParams p) {
+    __shared__ double red[QR_NP];
+    __shared__ double wsum[QR_THREADS / 32][QR_NP];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x, jb = p.jb;
+    const long long r_begin = p.j0 + (long long)blockIdx.x * p.rows_per_cta;
+    long long r_end = r_begin + p.rows_per_cta;
+    if (r_end > p.M) r_end = p.M;
+    double* Ap = p.A + p.j0;                     // column offset of the panel
+
+    double part[QR_NP];
+    // ---- dots for column 0
+#pragma unroll
+    for (int c = 0; c < QR_NP; ++c) part[c] = 0.0;
+    for (long long i = r_begin + tid; i < r_end; i += QR_THREADS) {
+        if (i > p.j0) {
+            const double* row = Ap + i * p.lda;
+            const double x = row[0];
+            part[0] = fma(x, x, part[0]);
+#pragma unroll
+            for (int c = 1; c < QR_NB; ++c)
+                if (c < jb) part[1 + c] = fma(x, row[c], part[1 + c]);
+        }
+    }
+
+    for (int j = 0; j < jb; ++j) {
+        // ---- publish this CTA's partial sums for column j, then meet at the barrier
+#pragma unroll
+        for (int c = 0; c < QR_NP; ++c) {
+            const double v = warp_sum(part[c]);
+            if (lane == 0) wsum[wid][c] = v;
+        }
+        __syncthreads();
+        double* mypart = p.gpart + ((size_t)(j & 1) * G + blockIdx.x) * QR_NP;
+        if (tid < QR_NP) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < QR_THREADS / 32; ++q) acc += wsum[q][tid];
+            mypart[tid] = acc;
+        }
+        grid_barrier(p.counter, (unsigned int)(j + 1) * G);
+        if (tid < QR_NP) {
+            const double* gp = p.gpart + (size_t)(j & 1) * G * QR_NP + tid;
+            double acc = 0.0;
+            for (int b = 0; b < G; ++b) acc += __ldcg(gp + (size_t)b * QR_NP);
+            red[tid] = acc;
+        }
+        __syncthreads();
+
+        // ---- reflector j (LAPACK dlarfg): beta = -sign(alpha)|x|, tau = (beta-alpha)/beta, v = x/(alpha-beta)
+        const long long dj = p.j0 + j;
+        const double* drow = Ap + dj * p.lda;
+        const double alpha = __ldcg(drow + j);
+        const double sigma = red[0];
+        double beta = alpha, tau = 0.0, scale = 0.0;
+        if (sigma != 0.0) {
+            const double nrm = sqrt(fma(alpha, alpha, sigma));
+            beta = alpha >= 0.0 ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        double wv[QR_NB];      // tau * (v^T A[:, c]) for c > j
+#pragma unroll
+        for (int c = 0; c < QR_NB; ++c) {
+            wv[c] = 0.0;
+            if (c > j && c < jb) wv[c] = tau * fma(scale, red[1 + c], __ldcg(drow + c));
+        }
+        if (blockIdx.x == 0 && tid == 0) p.tau[j] = tau;
+
+        // ---- apply to my rows; gather the dots of column j+1 on the fly
+#pragma unroll
+        for (int c = 0; c < QR_NP; ++c) part[c] = 0.0;
+        for (long long i = r_begin + tid; i < r_end; i += QR_THREADS) {
+            if (i < dj) continue;
+            double* row = Ap + i * p.lda;
+            if (i == dj) {
+                row[j] = beta;
+#pragma unroll
+                for (int c = 0; c < QR_NB; ++c)
+                    if (c > j && c < jb) row[c] -= wv[c];
+            } else {
+                const double v = row[j] * scale;
+                row[j] = v;
+                double a[QR_NB];
+#pragma unroll
+                for (int c = 0; c < QR_NB; ++c) {
+                    a[c] = 0.0;
+                    if (c > j && c < jb) { a[c] = fma(-v, wv[c], row[c]); row[c] = a[c]; }
+                }
+                if (i > dj + 1 && j + 1 < jb) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int c = 0; c < QR_NB; ++c) if (c == j + 1) x = a[c];
+                    part[0] = fma(x, x, part[0]);
+#pragma unroll
+                    for (int c = 0; c < QR_NB; ++c)
+                        if (c > j + 1 && c < jb) part[1 + c] = fma(x, a[c], part[1 + c]);
+                }
+            }
+        }
+    }
+}
+
+// ---- Gram of the panel's reflectors: Gpart[cta][16][16] = sum_rows V[i][a] V[i][b]
+struct VView {
+    const double* A; long long lda; long long j0; int jb;
+    // V[i][a] for global row i (>= j0): implicit unit diagonal / zeros above it
+    __device__ __forceinline__ double at(long long i, int a) const {
+        if (a >= jb) return 0.0;
+        const long long d = j0 + a;
+        if (i > d) return A[i * lda + d];
+        return i == d ? 1.0 : 0.0;
+    }
+};
+
+constexpr int QR_TR = 64;   // rows per staged V tile
+
+__device__ __forceinline__ void stage_v(double (*vt)[QR_NB], const VView& V, long long row0, long long M) {
+    for (int idx = threadIdx.x; idx < QR_TR * QR_NB; idx += blockDim.x) {
+        const int r = idx / QR_NB, a = idx % QR_NB;
+        const long long i = row0 + r;
+        vt[r][a] = i < M ? V.at(i, a) : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(QR_THREADS) qr_gram_kernel(VView V, long long M, long long rows_per_cta,
+                                                             double* gpart) {
+    __shared__ __align__(16) double vt[QR_TR][QR_NB];
+    const int a = threadIdx.x / QR_NB, b = threadIdx.x % QR_NB;
+    const long long r_begin = V.j0 + (long long)blockIdx.x * rows_per_cta;
+    long long r_end = r_begin + rows_per_cta;
+    if (r_end > M) r_end = M;
+    double acc = 0.0;
+    for (long long row0 = r_begin; row0 < r_end; row0 += QR_TR) {
+        __syncthreads();
+        stage_v(vt, V, row0, r_end);
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < QR_TR; ++r) acc = fma(vt[r][a], vt[r][b], acc);
+    }
+    gpart[(size_t)blockIdx.x * QR_NB * QR_NB + threadIdx.x] = acc;
+}
+
+// T (upper triangular, jb x jb, stored 16 x 16 row-major): T[j][j] = tau_j,
+// T[0:j, j] = -tau_j * T[0:j, 0:j] * (V[:, 0:j]^T v_j)      (LAPACK dlarft, forward / columnwise)
+__global__ void __launch_bounds__(QR_THREADS) qr_build_t_kernel(const double* gpart, int nparts, const double* tau,
+                                                                int jb, double* T) {
+    __shared__ double G[QR_NB][QR_NB];
+    __shared__ double Ts[QR_NB][QR_NB];
+    double acc = 0.0;
+    for (int b = 0; b < nparts; ++b) acc += gpart[(size_t)b * QR_NB * QR_NB + threadIdx.x];
+    G[threadIdx.x / QR_NB][threadIdx.x % QR_NB] = acc;
+    Ts[threadIdx.x / QR_NB][threadIdx.x % QR_NB] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < jb; ++j) {
+            const double tj = tau[j];
+            Ts[j][j] = tj;
+            for (int r = 0; r < j; ++r) {
+                double s = 0.0;
+                for (int l = r; l < j; ++l) s = fma(Ts[r][l], G[l][j], s);
+                Ts[r][j] = -tj * s;
+            }
+        }
+    }
+    __syncthreads();
+    T[threadIdx.x] = Ts[threadIdx.x / QR_NB][threadIdx.x % QR_NB];
+}
+
+// ---- trailing update, step 1: Wpart[split][k][c] = sum_{rows in split} V[i][k] * C[i][c]
+struct TrailParams {
+    VView V; long long M;
+    double* C; long long ldc; long long nc;          // C = columns to update (pointer already offset)
+    long long rows_per_split; int splits;
+    double* wpart;                                    // [splits][16][nc]
+    const double* T; int t_transpose;                 // apply T^T (QR) or T (forming Q)
+};
+
+__global__ void __launch_bounds__(QR_THREADS) qr_trail_w_kernel(const TrailParams p) {
+    __shared__ __align__(16) double vt[QR_TR][QR_NB];
+    const long long c = (long long)blockIdx.x * QR_THREADS + threadIdx.x;
+    const long long r_begin = p.V.j0 + (long long)blockIdx.y * p.rows_per_split;
+    long long r_end = r_begin + p.rows_per_split;
+    if (r_end > p.M) r_end = p.M;
+    double acc[QR_NB];
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) acc[k] = 0.0;
+    for (long long row0 = r_begin; row0 < r_end; row0 += QR_TR) {
+        __syncthreads();
+        stage_v(vt, p.V, row0, r_end);
+        __syncthreads();
+        if (c < p.nc) {
+            const int lim = (int)min((long long)QR_TR, r_end - row0);
+            for (int r = 0; r < lim; ++r) {
+                const double x = p.C[(row0 + r) * p.ldc + c];
+                const double2* v2 = reinterpret_cast<const double2*>(vt[r]);
+#pragma unroll
+                for (int k = 0; k < QR_NB / 2; ++k) {
+                    const double2 vv = v2[k];
+                    acc[2 * k] = fma(vv.x, x, acc[2 * k]);
+                    acc[2 * k + 1] = fma(vv.y, x, acc[2 * k + 1]);
+                }
+            }
+        }
+    }
+    if (c < p.nc) {
+#pragma unroll
+        for (int k = 0; k < QR_NB; ++k) p.wpart[((size_t)blockIdx.y * QR_NB + k) * p.nc + c] = acc[k];
+    }
+}
+
+// ---- step 2: W = op(T) * sum_splits Wpart ;  C -= V W
+__global__ void __launch_bounds__(QR_THREADS) qr_trail_apply_kernel(const TrailParams p) {
+    __shared__ __align__(16) double vt[QR_TR][QR_NB];
+    __shared__ double Ts[QR_NB][QR_NB];
+    const long long c = (long long)blockIdx.x * QR_THREADS + threadIdx.x;
+    const long long r_begin = p.V.j0 + (long long)blockIdx.y * p.rows_per_split;
+    long long r_end = r_begin + p.rows_per_split;
+    if (r_end > p.M) r_end = p.M;
+    Ts[threadIdx.x / QR_NB][threadIdx.x % QR_NB] = p.T[threadIdx.x];
+    __syncthreads();
+    double w[QR_NB], w2[QR_NB];
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) {
+        double s = 0.0;
+        if (c < p.nc)
+            for (int sp = 0; sp < p.splits; ++sp) s += p.wpart[((size_t)sp * QR_NB + k) * p.nc + c];
+        w[k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) {
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < QR_NB; ++l) s = fma(p.t_transpose ? Ts[l][k] : Ts[k][l], w[l], s);
+        w2[k] = s;
+    }
+    for (long long row0 = r_begin; row0 < r_end; row0 += QR_TR) {
+        __syncthreads();
+        stage_v(vt, p.V, row0, r_end);
+        __syncthreads();
+        if (c < p.nc) {
+            const int lim = (int)min((long long)QR_TR, r_end - row0);
+            for (int r = 0; r < lim; ++r) {
+                double* dst = p.C + (row0 + r) * p.ldc + c;
+                const double2* v2 = reinterpret_cast<const double2*>(vt[r]);
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < QR_NB / 2; ++k) {
+                    const double2 vv = v2[k];
+                    s = fma(vv.x, w2[2 * k], s);
+                    s = fma(vv.y, w2[2 * k + 1], s);
+                }
+                *dst -= s;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) qr_eye_kernel(double* Q, long long M, long long K, long long ldq) {
+    const long long total = M * K;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / K, c = idx - r * K;
+        Q[r * ldq + c] = (r == c) ? 1.0 : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct QrWs {
+    unsigned int* counter;   // 64 B
+    double* gpart;           // panel partials: 2 * sms * QR_NP
+    double* gram;            // sms * 256
+    double* T;               // 256
+    double* wpart;           // splits * 16 * ncols
+    int max_splits;
+};
+
+static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
+    const int sms = num_sms();
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_counter = take(256);
+    const size_t o_gpart = take((size_t)2 * sms * QR_NP * 8);
+    const size_t o_gram = take((size_t)sms * QR_NB * QR_NB * 8);
+    const size_t o_T = take(QR_NB * QR_NB * 8);
+    int max_splits = (int)((M + 1023) / 1024);
+    if (max_splits > 2 * sms) max_splits = 2 * sms;
+    if (max_splits < 1) max_splits = 1;
+    const size_t o_w = take((size_t)max_splits * QR_NB * (size_t)(N > 0 ? N : 1) * 8);
+    if (out) {
+        char* b = (char*)base;
+        out->counter = (unsigned int*)(b + o_counter);
+        out->gpart = (double*)(b + o_gpart);
+        out->gram = (double*)(b + o_gram);
+        out->T = (double*)(b + o_T);
+        out->wpart = (double*)(b + o_w);
+        out->max_splits = max_splits;
+    }
+    return off;
+}
+
+static int run_panel(double* A, long long lda, long long M, long long j0, int jb, double* tau, const QrWs& w,
+                     cudaStream_t st) {
+    const long long rows = M - j0;
+    int G = (int)((rows + QR_THREADS - 1) / QR_THREADS);
+    const int sms = num_sms();
+    if (G > sms) G = sms;
+    if (G < 1) G = 1;
+    PanelParams pp;
+    pp.A = A; pp.lda = lda; pp.M = M; pp.j0 = j0; pp.jb = jb; pp.tau = tau + j0; pp.gpart = w.gpart;
+    pp.counter = w.counter; pp.rows_per_cta = (rows + G - 1) / G;
+    PLA_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st));
+    void* args[] = {(void*)&pp};
+    PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
+    // compact-WY factor T
+    int GG = (int)((rows + 4 * QR_TR - 1) / (4 * QR_TR));
+    if (GG > sms) GG = sms;
+    if (GG < 1) GG = 1;
+    VView V{A, lda, j0, jb};
+    qr_gram_kernel<<<GG, QR_THREADS, 0, st>>>(V, M, (rows + GG - 1) / GG, w.gram);
+    PLA_LAUNCH_CHECK();
+    qr_build_t_kernel<<<1, QR_THREADS, 0, st>>>(w.gram, GG, tau + j0, jb, w.T);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+// C[j0:M, 0:nc] <- (I - V op(T) V^T) C   with V the reflectors of panel (j0, jb)
+static int run_trailing(const double* Afac, long long lda, long long M, long long j0, int jb, double* C,
+                        long long ldc, long long nc, int t_transpose, const QrWs& w, cudaStream_t st) {
+    if (nc <= 0) return 0;
+    const long long rows = M - j0;
+    const int sms = num_sms();
+    const int col_blocks = (int)((nc + QR_THREADS - 1) / QR_THREADS);
+    long long want = (2LL * sms + col_blocks - 1) / col_blocks;       // ~2 CTAs per SM
+    long long by_rows = (rows + 4 * QR_TR - 1) / (4 * QR_TR);         // >= 256 rows per split
+    int splits = (int)(want < by_rows ? want : by_rows);
+    if (splits > w.max_splits) splits = w.max_splits;
+    if (splits < 1) splits = 1;
+    TrailParams tp;
+    tp.V = VView{Afac, lda, j0, jb}; tp.M = M; tp.C = C; tp.ldc = ldc; tp.nc = nc;
+    tp.rows_per_split = (rows + splits - 1) / splits;
+    tp.splits = (int)((rows + tp.rows_per_split - 1) / tp.rows_per_split);
+    tp.wpart = w.wpart; tp.T = w.T; tp.t_transpose = t_transpose;
+    dim3 grid(col_blocks, tp.splits);
+    qr_trail_w_kernel<<<grid, QR_THREADS, 0, st>>>(tp);
+    PLA_LAUNCH_CHECK();
+    qr_trail_apply_kernel<<<grid, QR_THREADS, 0, st>>>(tp);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pla
+
+using namespace pla;
+
+extern "C" size_t pla_qr_workspace_bytes(int64_t M, int64_t N) { return qr_ws_layout(M, N, nullptr, nullptr); }
+
+extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64_t ncols_factor, double* tau,
+                             void* ws, size_t ws_bytes, void* stream) {
+    PLA_CHECK_ARG(A != nullptr, 1, "A is null");
+    PLA_CHECK_ARG(M >= 1 && N >= 1, 2, "empty matrix");
+    PLA_CHECK_ARG(lda >= N, 4, "lda < N");
+    PLA_CHECK_ARG(ncols_factor >= 1 && ncols_factor <= N && ncols_factor <= M, 5, "ncols_factor out of range");
+    PLA_CHECK_ARG(tau != nullptr, 6, "tau is null");
+    PLA_CHECK_ARG(ws != nullptr && ws_bytes >= pla_qr_workspace_bytes(M, N), 8, "workspace too small");
+    QrWs w;
+    qr_ws_layout(M, N, ws, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (long long j0 = 0; j0 < ncols_factor; j0 += QR_NB) {
+        const int jb = (int)((ncols_factor - j0) < QR_NB ? (ncols_factor - j0) : QR_NB);
+        int rc = run_panel(A, lda, M, j0, jb, tau, w, st);
+        if (rc) return rc;
+        const long long nc = N - (j0 + jb);
+        rc = run_trailing(A, lda, M, j0, jb, A + j0 + jb, lda, nc, /*T^T*/ 1, w, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int pla_orgqr_f64(const double* A, int64_t M, int64_t K, int64_t lda, const double* tau, double* Q,
+                             int64_t ldq, void* ws, size_t ws_bytes, void* stream) {
+    PLA_CHECK_ARG(A != nullptr, 1, "A is null");
+    PLA_CHECK_ARG(M >= 1 && K >= 1 && K <= M, 3, "need 1 <= K <= M");
+    PLA_CHECK_ARG(lda >= K, 4, "lda < K");
+    PLA_CHECK_ARG(tau != nullptr && Q != nullptr && ldq >= K, 6, "bad tau / Q / ldq");
+    PLA_CHECK_ARG(ws != nullptr && ws_bytes >= pla_qr_workspace_bytes(M, K), 9, "workspace too small");
+    QrWs w;
+    qr_ws_layout(M, K, ws, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = num_sms();
+    qr_eye_kernel<<<4 * sms, 256, 0, st>>>(Q, M, K, ldq);
+    PLA_LAUNCH_CHECK();
+    // Q = H_1 H_2 ... H_p [I; 0]: apply the panels last to first; panel j0 only touches columns >= j0
+    const long long last = ((K - 1) / QR_NB) * QR_NB;
+    for (long long j0 = last; j0 >= 0; j0 -= QR_NB) {
+        const int jb = (int)((K - j0) < QR_NB ? (K - j0) : QR_NB);
+        VView V{A, lda, j0, jb};
+        const long long rows = M - j0;
+        int GG = (int)((rows + 4 * QR_TR - 1) / (4 * QR_TR));
+        if (GG > sms) GG = sms;
+        if (GG < 1) GG = 1;
+        qr_gram_kernel<<<GG, QR_THREADS, 0, st>>>(V, M, (rows + GG - 1) / GG, w.gram);
+        PLA_LAUNCH_CHECK();
+        qr_build_t_kernel<<<1, QR_THREADS, 0, st>>>(w.gram, GG, tau + j0, jb, w.T);
+        PLA_LAUNCH_CHECK();
+        int rc = run_trailing(A, lda, M, j0, jb, Q + j0, ldq, K - j0, /*T*/ 0, w, st);
+        if (rc) return rc;
+    }
+    return 0;
+}

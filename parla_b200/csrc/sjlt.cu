@@ -1,0 +1,307 @@
+// K2: SJLT sketch  out[d x n] = scale * S @ A  for a sparse sign operator with k nonzeros per column.
+//
+// Replaces scipy.sparse csc_matvecs behind `S @ A` / `S @ b` (parla/drivers/least_squares.py:303,314)
+// for the operator built by parla/utils/sketching.py:51-74.
+//
+// Formulation: destination-major gather.  A one-off plan turns the column-wise index form into CSR
+// (per destination row: the list of (source row, sign), sorted by source row).  One warp then owns
+// (destination row, 256-column chunk): it walks its list, reads 2 KB contiguous pieces of the source
+// rows (coalesced), accumulates in registers and writes each output element exactly once -- no
+// atomics, no shared-memory read-modify-write, fixed summation order (deterministic).  Tasks are
+// ordered chunk-major and every list is sorted by source row, so the k readers of a source-row piece
+// run close together in time and share it through the 126 MB L2.
+#include "common.cuh"
+#include "philox.cuh"
+#include "../../include/parla_b200.h"
+
+namespace pla {
+
+constexpr long long SJ_MAGIC = 0x504C41534A4C5431LL;   // "PLASJLT1"
+constexpr int SJ_SORT_MAX = 8192;                      // per-destination segment sorted in smem up to this
+
+struct SjltPlanHeader { long long magic, nnz, bad_index_count, pad; };
+
+__global__ void __launch_bounds__(256) sjlt_count_kernel(const int32_t* __restrict__ rows, long long nnz, long long d,
+                                                         unsigned long long* counts, SjltPlanHeader* hdr) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = rows[e];
+        if (r < 0 || r >= d) atomicAdd((unsigned long long*)&hdr->bad_index_count, 1ULL);
+        else atomicAdd(&counts[r], 1ULL);
+    }
+}
+
+// exclusive scan of counts[d] -> offsets[d+1] (single CTA, chunked)
+__global__ void __launch_bounds__(1024) sjlt_scan_kernel(const unsigned long long* __restrict__ counts, long long d,
+                                                         long long* offsets) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < d; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const long long v = i < d ? (long long)counts[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            long long w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            wsum[lane] = w;     // inclusive over warps
+        }
+        __syncthreads();
+        const long long before = carry + (wid > 0 ? wsum[wid - 1] : 0) + incl - v;
+        if (i < d) offsets[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[d] = carry;
+}
+
+__global__ void __launch_bounds__(256) sjlt_fill_kernel(const int32_t* __restrict__ rows, const int8_t* __restrict__ signs,
+                                                        long long nnz, long long k, long long d,
+                                                        const long long* __restrict__ offsets,
+                                                        unsigned long long* cursor, int32_t* entries) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = rows[e];
+        if (r < 0 || r >= d) continue;
+        const long long src = e / k;
+        const unsigned long long slot = atomicAdd(&cursor[r], 1ULL);
+        entries[offsets[r] + (long long)slot] = (int32_t)((src << 1) | (signs[e] < 0 ? 1 : 0));
+    }
+}
+
+// sort each destination's segment by packed entry (= by source row): bitonic sort in shared memory
+__global__ void __launch_bounds__(256) sjlt_segsort_kernel(const long long* __restrict__ offsets, int32_t* entries) {
+    extern __shared__ int32_t seg[];
+    const long long beg = offsets[blockIdx.x], end = offsets[blockIdx.x + 1];
+    const int len = (int)(end - beg);
+    if (len <= 1 || len > SJ_SORT_MAX) return;
+    int np2 = 1;
+    while (np2 < len) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) seg[i] = i < len ? entries[beg + i] : 0x7fffffff;
+    __syncthreads();
+    for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const int32_t a = seg[lo], b = seg[hi];
+                if ((a > b) == up) { seg[lo] = b; seg[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < len; i += blockDim.x) entries[beg + i] = seg[i];
+}
+
+// ---- apply: warp <-> (destination row, column chunk of 32*VEC*J columns)
+template <int VEC, int J>
+__global__ void __launch_bounds__(256) sjlt_apply_kernel(const long long* __restrict__ offsets,
+                                                         const int32_t* __restrict__ entries, long long d,
+                                                         const double* __restrict__ A, long long n, long long lda,
+                                                         const double* __restrict__ bvec, double scale, double* out,
+                                                         long long ldo, double* out_b, long long ldob,
+                                                         int accumulate, long long nchunks) {
+    constexpr int CW = 32 * VEC * J;                    // chunk width in columns
+    const int lane = threadIdx.x & 31;
+    const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (task >= nchunks * d) return;
+    const long long chunk = task / d, r = task - chunk * d;
+    const long long c0 = chunk * CW;
+    const long long beg = offsets[r], end = offsets[r + 1];
+    double acc[J * VEC];
+#pragma unroll
+    for (int j = 0; j < J * VEC; ++j) acc[j] = 0.0;
+    double bacc = 0.0;
+    const bool do_b = (bvec != nullptr) && (chunk == 0);
+
+    for (long long e0 = beg; e0 < end; e0 += 32) {
+        const long long me = e0 + lane;
+        const int32_t ent = me < end ? entries[me] : 0;
+        if (do_b && me < end) {
+            const double bv = bvec[ent >> 1];
+            bacc += (ent & 1) ? -bv : bv;
+        }
+        const int cnt = (int)min(32LL, end - e0);
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const int32_t en = __shfl_sync(0xffffffffu, ent, t);
+            const double* src = A + (long long)(en >> 1) * lda + c0;
+            const double sg = (en & 1) ? -1.0 : 1.0;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const long long c = (long long)VEC * (lane + 32 * j);
+                if (c0 + c < n) {
+                    if (VEC == 2) {
+                        const double2 a = __ldg(reinterpret_cast<const double2*>(src + c));
+                        acc[j * VEC] = fma(sg, a.x, acc[j * VEC]);
+                        acc[j * VEC + VEC - 1] = fma(sg, a.y, acc[j * VEC + VEC - 1]);
+                    } else {
+                        acc[j * VEC] = fma(sg, __ldg(src + c), acc[j * VEC]);
+                    }
+                }
+            }
+        }
+    }
+    double* dst = out + r * ldo + c0;
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const long long c = (long long)VEC * (lane + 32 * j) + v;
+            if (c0 + c < n) {
+                const double val = scale * acc[j * VEC + v];
+                dst[c] = accumulate ? dst[c] + val : val;
+            }
+        }
+    if (do_b && out_b != nullptr) {
+        bacc = warp_sum(bacc);
+        if (lane == 0) out_b[r * ldob] = accumulate ? out_b[r * ldob] + scale * bacc : scale * bacc;
+    }
+}
+
+// ---- native operator: k distinct rows per column from Philox (see oracle/philox_ref.py: sjlt_columns)
+__global__ void __launch_bounds__(256) sjlt_generate_kernel(long long d, long long m, int k, uint64_t seed,
+                                                            long long col_offset, int32_t* rows, int8_t* signs) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        const uint64_t gi = (uint64_t)(col_offset + i);
+        uint32_t call = 0;
+        Philox4 o = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), call, 0x534A4C54u, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+        uint32_t words[4] = {o.x, o.y, o.z, o.w};
+        int wi = 1;                                   // words[0] = sign bits
+        const uint32_t sbits = words[0];
+        int32_t picked[32];
+        for (int q = 0; q < k; ++q) {
+            int32_t cand;
+            bool dup;
+            do {
+                if (wi == 4) {
+                    ++call;
+                    o = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), call, 0x534A4C54u, (uint32_t)seed,
+                                      (uint32_t)(seed >> 32));
+                    words[0] = o.x; words[1] = o.y; words[2] = o.z; words[3] = o.w;
+                    wi = 0;
+                }
+                cand = (int32_t)(((uint64_t)words[wi++] * (uint64_t)d) >> 32);
+                dup = false;
+                if (d >= k)
+                    for (int t = 0; t < q; ++t) dup |= (picked[t] == cand);
+            } while (dup);
+            picked[q] = cand;
+            rows[i * k + q] = cand;
+            signs[i * k + q] = ((sbits >> q) & 1u) ? (int8_t)-1 : (int8_t)1;
+        }
+    }
+}
+
+}  // namespace pla
+
+using namespace pla;
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" size_t pla_sjlt_plan_bytes(int64_t d, int64_t m, int64_t k) {
+    return align256(sizeof(SjltPlanHeader)) + align256((size_t)(d + 1) * 8) + align256((size_t)m * k * 4);
+}
+extern "C" size_t pla_sjlt_plan_workspace_bytes(int64_t d, int64_t m, int64_t k) {
+    (void)m; (void)k;
+    return 2 * align256((size_t)d * 8);
+}
+
+extern "C" int pla_sjlt_plan_f64(const int32_t* rows, const int8_t* signs, int64_t m, int64_t k, int64_t d,
+                                 void* plan, void* ws, size_t ws_bytes, void* stream) {
+    PLA_CHECK_ARG(rows != nullptr && signs != nullptr, 1, "null index arrays");
+    PLA_CHECK_ARG(m >= 1 && m < (1LL << 30), 3, "m out of range (1 .. 2^30-1)");
+    PLA_CHECK_ARG(k >= 1 && k <= 32, 4, "k out of range (1..32)");
+    PLA_CHECK_ARG(d >= 1, 5, "d < 1");
+    PLA_CHECK_ARG(plan != nullptr, 6, "plan is null");
+    PLA_CHECK_ARG(ws != nullptr && ws_bytes >= pla_sjlt_plan_workspace_bytes(d, m, k), 8, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* pb = (char*)plan;
+    SjltPlanHeader* hdr = (SjltPlanHeader*)pb;
+    long long* offsets = (long long*)(pb + align256(sizeof(SjltPlanHeader)));
+    int32_t* entries = (int32_t*)(pb + align256(sizeof(SjltPlanHeader)) + align256((size_t)(d + 1) * 8));
+    unsigned long long* counts = (unsigned long long*)ws;
+    unsigned long long* cursor = (unsigned long long*)((char*)ws + align256((size_t)d * 8));
+    const long long nnz = m * k;
+    SjltPlanHeader h{SJ_MAGIC, nnz, 0, 0};
+    PLA_CUDA(cudaMemcpyAsync(hdr, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    PLA_CUDA(cudaMemsetAsync(ws, 0, 2 * align256((size_t)d * 8), st));
+    int nb = (int)((nnz + 255) / 256);
+    if (nb > 16 * num_sms()) nb = 16 * num_sms();
+    sjlt_count_kernel<<<nb, 256, 0, st>>>(rows, nnz, d, counts, hdr);
+    PLA_LAUNCH_CHECK();
+    sjlt_scan_kernel<<<1, 1024, 0, st>>>(counts, d, offsets);
+    PLA_LAUNCH_CHECK();
+    sjlt_fill_kernel<<<nb, 256, 0, st>>>(rows, signs, nnz, k, d, offsets, cursor, entries);
+    PLA_LAUNCH_CHECK();
+    PLA_CUDA(cudaFuncSetAttribute(sjlt_segsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SJ_SORT_MAX * 4));
+    sjlt_segsort_kernel<<<(unsigned)d, 256, SJ_SORT_MAX * 4, st>>>(offsets, entries);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pla_sjlt_apply_f64(const void* plan, int64_t d, int64_t m, int64_t k, const double* A, int64_t n,
+                                  int64_t lda, const double* bvec, double scale, double* out, int64_t ldo,
+                                  double* out_b, int64_t ldob, int accumulate, void* stream) {
+    PLA_CHECK_ARG(plan != nullptr, 1, "plan is null");
+    PLA_CHECK_ARG(d >= 1 && m >= 1 && k >= 1, 2, "bad dims");
+    PLA_CHECK_ARG(A != nullptr && n >= 1 && lda >= n, 5, "bad A / n / lda");
+    PLA_CHECK_ARG(out != nullptr && ldo >= n, 10, "bad out / ldo");
+    PLA_CHECK_ARG(bvec == nullptr || (out_b != nullptr && ldob >= 1), 12, "out_b is null / ldob < 1");
+    const char* pb = (const char*)plan;
+    const long long* offsets = (const long long*)(pb + align256(sizeof(SjltPlanHeader)));
+    const int32_t* entries = (const int32_t*)(pb + align256(sizeof(SjltPlanHeader)) + align256((size_t)(d + 1) * 8));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec2 = (n % 2 == 0) && (lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const int warps_per_cta = 8;
+    if (vec2) {
+        const long long cw = 256, nchunks = (n + cw - 1) / cw;
+        const long long ctas = (nchunks * d + warps_per_cta - 1) / warps_per_cta;
+        sjlt_apply_kernel<2, 4><<<(unsigned)ctas, 256, 0, st>>>(offsets, entries, d, A, n, lda, bvec, scale, out, ldo,
+                                                               out_b, ldob, accumulate, nchunks);
+    } else {
+        const long long cw = 128, nchunks = (n + cw - 1) / cw;
+        const long long ctas = (nchunks * d + warps_per_cta - 1) / warps_per_cta;
+        sjlt_apply_kernel<1, 4><<<(unsigned)ctas, 256, 0, st>>>(offsets, entries, d, A, n, lda, bvec, scale, out, ldo,
+                                                               out_b, ldob, accumulate, nchunks);
+    }
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pla_sjlt_plan_status(const void* plan, int64_t* bad_index_count_host) {
+    PLA_CHECK_ARG(plan != nullptr && bad_index_count_host != nullptr, 1, "null argument");
+    SjltPlanHeader h;
+    PLA_CUDA(cudaMemcpy(&h, plan, sizeof(h), cudaMemcpyDeviceToHost));   // synchronising: debug / validation only
+    if (h.magic != SJ_MAGIC) { set_error("pla_sjlt_plan_status: not a plan"); return -1; }
+    *bad_index_count_host = h.bad_index_count;
+    return 0;
+}
+
+extern "C" int pla_sjlt_generate(int64_t d, int64_t m, int64_t k, uint64_t seed, int64_t col_offset, int32_t* rows,
+                                 int8_t* signs, void* stream) {
+    PLA_CHECK_ARG(d >= 1 && d < (1LL << 31), 1, "d out of range");
+    PLA_CHECK_ARG(m >= 1, 2, "m < 1");
+    PLA_CHECK_ARG(k >= 1 && k <= 32, 3, "k out of range (1..32)");
+    PLA_CHECK_ARG(col_offset >= 0, 5, "col_offset < 0");
+    PLA_CHECK_ARG(rows != nullptr && signs != nullptr, 6, "null outputs");
+    int nb = (int)((m + 255) / 256);
+    if (nb > 16 * num_sms()) nb = 16 * num_sms();
+    sjlt_generate_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(d, m, (int)k, seed, col_offset, rows, signs);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}

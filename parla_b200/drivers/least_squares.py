@@ -1,0 +1,229 @@
+"""Sketch-and-precondition / sketch-and-solve drivers for over-determined least squares on B200.
+
+Mirrors parla/drivers/least_squares.py: ``OverLstsqSolver`` (:16-86), ``dim_checks`` (:89-104),
+``SSO1`` (:114-189) and ``SPO`` (:206-369; "SAP1" == mode 'qr', "SAP2" == mode 'svd').  Same
+constructor and ``__call__(A, b, delta, tol, iter_lim, rng, logging=True)`` signatures; ``A`` / ``b``
+are torch CUDA fp64 tensors (or ``parallel.RowSharded`` shards, or numpy arrays which are uploaded
+and whose result is returned as numpy).  ``exec`` is an alias of ``__call__`` (RandLAPACK naming).
+
+What differs from the reference's execution, not from its mathematics:
+  * ``S @ A`` and ``S @ b`` are one kernel writing ``[A_ske | b_ske]`` into one d x (n+1) buffer; the
+    Householder QR of its first n columns then leaves ``Q^T b_ske`` in the last column
+    (least_squares.py:311-315 in one factorisation, Q never formed);
+  * the presolve residual ``A x_ske - b`` (:344) IS LSQR's initial residual (lsqr.py:367-370), so it is
+    computed once and handed to the iterative solver;
+  * ``y = b - A x`` (saddle.py:199) and ``A^T b`` for the log (:361) share one pass over A.
+"""
+import math
+import time
+import warnings
+
+import numpy as np
+import torch
+
+from .. import kernels as K
+from ..comps.determiter.logging import SketchAndPrecondLog
+from ..comps.determiter import saddle as dsad
+from ..comps import preconditioning as rpc
+from ..parallel import RowSharded, allreduce_, unwrap
+from ..utils.sketching import as_device_operator, shard_context
+
+F64 = torch.float64
+
+
+class OverLstsqSolver:
+    """min ||A x - b||_2^2 + delta ||x||_2^2 for a tall A.  Interface of least_squares.py:16-86."""
+
+    def __call__(self, A, b, delta, tol, iter_lim, rng):
+        raise NotImplementedError()
+
+    exec = __call__
+
+
+def dim_checks(sampling_factor, n_rows, n_cols):
+    """least_squares.py:89-104."""
+    assert n_rows >= n_cols
+    d = int(sampling_factor * n_cols)
+    if d > n_rows:
+        msg = f"""
+        The embedding dimension "d" should not be larger than the
+        number of rows of the data matrix. Here, an embedding dimension
+        of d={d} has been requested for a matrix with only {n_rows} rows.
+        We will proceed by setting d={n_rows}. This parameter choice will
+        result in a very inefficient algorithm!
+        """
+        warnings.warn(msg)
+        d = n_rows
+    assert d >= n_cols
+    return d
+
+
+def _to_device(A, b):
+    """Accept numpy inputs (host buffers): upload, and remember to hand numpy back."""
+    host = isinstance(A, np.ndarray)
+    if host:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        A = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float64)).to(dev, non_blocking=True)
+        b = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(dev, non_blocking=True)
+    return A, b, host
+
+
+def _sketch(sketch_op_gen, d, A, b, delta, rng):
+    """[A_ske | b_ske] (+ ridge rows) in one (d [+ n]) x (n + 1) row-major buffer."""
+    A_loc, row_off, group = unwrap(A)
+    b_loc = unwrap(b)[0]
+    m, n = A.shape
+    with shard_context(row_off, A_loc.shape[0]):
+        S = as_device_operator(sketch_op_gen(d, m, rng), A_loc.device)
+    if S.shape[1] != A_loc.shape[0]:           # a full-width operator (e.g. a replayed reference S)
+        S = S.column_slice(row_off, A_loc.shape[0])
+    d_aug = d + (n if delta > 0 else 0)
+    W = torch.empty(d_aug, n + 1, dtype=F64, device=A_loc.device)
+    S.sketch_into(A_loc, b_loc, W[:d], row_offset=row_off)
+    allreduce_(W[:d], group)
+    if delta > 0:
+        W[d:, :].zero_()
+        W[d:, :n].diagonal().fill_(math.sqrt(delta))
+    return S, W
+
+
+class SSO1(OverLstsqSolver):
+    """Sketch-and-solve (least_squares.py:114-189): x = argmin ||S A x - S b||, via Householder QR."""
+
+    def __init__(self, sketch_op_gen, sampling_factor, lapack_driver=None, overwrite_sketch=True):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+        self.lapack_driver = lapack_driver
+        self.overwrite_sketch = overwrite_sketch
+
+    def __call__(self, A, b, delta, tol, iter_lim, rng, logging=True):
+        if not np.isnan(tol):
+            warnings.warn("""
+            This OverLstsqSolver implementation cannot directly control
+            approximation error. Parameter "tol" is being ignored.
+            """)
+        if iter_lim > 1:
+            warnings.warn("""
+            This OverLstsqSolver implementation is not iterative.
+            Parameter "iter_lim" is being ignored.
+            """)
+        A, b, host = _to_device(A, b)
+        n_rows, n_cols = A.shape
+        d = dim_checks(self.sampling_factor, n_rows, n_cols)
+        rng = np.random.default_rng(rng)
+        log = {'time_sketch': -1.0, 'time_solve': -1.0}
+        quick_time = _clock(logging)
+        tic = quick_time()
+        _, W = _sketch(self.sketch_op_gen, d, A, b, delta, rng)
+        log['time_sketch'] = quick_time() - tic
+        tic = quick_time()
+        K.geqrf(W, n_cols)
+        x_ske = K.trsv_upper(W[:n_cols, :n_cols], W[:n_cols, n_cols].contiguous())
+        log['time_solve'] = quick_time() - tic
+        return (x_ske.cpu().numpy() if host else x_ske), log
+
+    exec = __call__
+
+
+def _clock(logging):
+    if not logging:
+        return lambda: 0
+    def now():
+        torch.cuda.synchronize()
+        return time.time()
+    return now
+
+
+class SPO(OverLstsqSolver):
+    """Sketch-and-precondition with LSQR (least_squares.py:206-369)."""
+
+    def __init__(self, sketch_op_gen, sampling_factor: int, mode='qr'):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+        self.mode = mode
+        self.iterative_solver = dsad.PcSS2()  # implements LSQR
+
+    def __call__(self, A, b, delta, tol, iter_lim, rng, logging=True):
+        A, b, host = _to_device(A, b)
+        n_rows, n_cols = A.shape
+        sqrt_delta = math.sqrt(delta)
+        d = dim_checks(self.sampling_factor, n_rows, n_cols)
+        rng = np.random.default_rng(rng)
+        A_loc, _, group = unwrap(A)
+        b_loc = unwrap(b)[0]
+        dev = A_loc.device
+
+        quick_time = _clock(logging)
+        log = SketchAndPrecondLog()
+
+        # Sketch the data matrix (and the right-hand side, same kernel)            :302-303, :314
+        tic = quick_time()
+        S, W = _sketch(self.sketch_op_gen, d, A, b, delta, rng)
+        log.time_sketch = quick_time() - tic
+
+        # Factor the sketch; sketch-and-solve presolve                              :306-341
+        n = n_cols
+        if self.mode == 'qr':
+            tic = quick_time()
+            K.geqrf(W, n)                                   # R = triu(W[:n,:n]), W[:, n] = Q^T [b_ske; 0]
+            R = W[:n, :n]
+            log.time_factor = quick_time() - tic
+            tic = quick_time()
+            z_ske = W[:n, n].contiguous()
+            tri = True
+        elif self.mode == 'chol':
+            tic = quick_time()
+            A_ske = W[:d, :n]
+            G = K.gemm(A_ske, A_ske, transa=True)
+            if delta > 0:
+                G.diagonal().add_(delta)
+            R = torch.linalg.cholesky(G, upper=True)        # small n x n factorisation: cuSOLVER glue
+            log.time_factor = quick_time() - tic
+            tic = quick_time()
+            g = K.rmatvec(A_ske, W[:d, n].contiguous())[:n]
+            z_ske = K.trsv_upper(R, g, trans=True)
+            tri = True
+        elif self.mode == 'svd':
+            tic = quick_time()
+            R, U, sigma, Vh = rpc.svd_right_precond(W[:, :n])
+            log.time_factor = quick_time() - tic
+            tic = quick_time()
+            z_ske = K.rmatvec(U[:d], W[:d, n].contiguous())[:R.shape[1]].clone()
+            tri = False
+        else:
+            raise ValueError()
+
+        # Presolve acceptance test (:344-352).  b - A x_ske is LSQR's starting residual, so the pass
+        # doubles as the solver's initialisation.
+        op = rpc.PrecondOperator(A, delta, R, tri)
+        bnorm = math.sqrt(float(allreduce_(K.sumsq(b_loc), group)))
+        warm = dict(u=b_loc.clone(),
+                    ub=torch.zeros(n, dtype=F64, device=dev) if delta > 0 else None,
+                    zss=torch.empty(n + 1, dtype=F64, device=dev),
+                    t=torch.empty(R.shape[1], dtype=F64, device=dev))
+        xw = torch.empty(n, dtype=F64, device=dev)
+        op.bidiag_pass(z_ske, warm["u"], warm["ub"], warm["zss"], xw, warm["t"], sa=-1.0, su=1.0)
+        rel_err = math.sqrt(float(warm["zss"][n])) / bnorm
+        if rel_err >= 1 or (rel_err > 1e-15 and R.shape[0] != R.shape[1]):
+            # Either the zero vector is a better solution, or we have an inconsistent
+            # rank-deficient problem (which forces us to initialize at the origin).
+            z_ske, warm = None, None
+        log.time_presolve = quick_time() - tic
+
+        # Iterative phase                                                           :355-358
+        tic = quick_time()
+        res = self.iterative_solver(A, b, None, delta, tol, iter_lim, R, tri, z_ske, _op=op, _warm=warm)
+        log.time_iterate = quick_time() - tic
+
+        if logging:                                                               # :360-367
+            ar0 = op.precond_t(op.atb)
+            iter_errors = res[2]
+            log.wrap_up(iter_errors, float(torch.linalg.vector_norm(ar0)))
+            log.error_desc = self.iterative_solver.ERROR_METRIC_INFO
+            log.iters = int(np.atleast_1d(iter_errors).size)
+            log.passes_over_A = op.passes + 1      # + the sketch
+        self.last_residual = res[1]
+        x = res[0]
+        return (x.cpu().numpy() if host else x), log
+
+    exec = __call__

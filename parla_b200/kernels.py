@@ -1,0 +1,289 @@
+"""Thin torch-tensor wrappers over the C ABI (``include/parla_b200.h``).
+
+PyTorch is used for device memory, streams and (elsewhere) ``torch.distributed`` only; every
+O(m n) operation below is a hand-written sm_100a kernel in ``libparla_b200.so``.  All wrappers
+enqueue on the caller's current CUDA stream and never synchronise (unless documented).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+PASS_DOT, PASS_AXPY, PASS_AXPY_G = 1, 2, 4
+PASS_MAX_N = 8192
+LSQR_NDOUBLE, LSQR_NINT = 32, 8
+LSQR_SA = 15            # dstate[15:17] = (sa, su) of the next pass
+F64 = torch.float64
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t, name, dtype=F64):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _rowmajor(t, name):
+    """Return (tensor, ld) for a 2-D row-major view (unit stride along columns)."""
+    _req(t, name)
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    if ld < t.shape[1]:
+        t = t.contiguous()
+        ld = t.shape[1]
+    return t, ld
+
+
+def _vec(t, name):
+    _req(t, name)
+    if t.dim() != 1:
+        raise ValueError(f"{name} must be 1-D")
+    return t if (t.numel() <= 1 or t.stride(0) == 1) else t.contiguous()
+
+
+class Workspace:
+    """Grow-only device scratch buffer (one per device), handed to the C ABI as (ptr, bytes)."""
+
+    _bufs = {}
+
+    @classmethod
+    def get(cls, device, nbytes, tag="main"):
+        key = (torch.device(device).index, tag)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def num_sms():
+    return _lib.load().pla_num_sms()
+
+
+# ---------------------------------------------------------------------------------------- K4
+def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None, flags=PASS_DOT, istop=None):
+    """One streaming read of A:  u <- sa*(A w) + su*u ;  z = A^T q ;  zss = [z, |u|^2].
+
+    Returns zss (n+1 doubles).  See pla_stream_pass_f64.
+    """
+    lib = _lib.load()
+    A, lda = _rowmajor(A, "A")
+    m, n = A.shape
+    if zss is None:
+        zss = torch.empty(n + 1, dtype=F64, device=A.device)
+    nb = lib.pla_stream_pass_workspace_bytes(m, n)
+    ws = Workspace.get(A.device, nb, "pass")
+    rc = lib.pla_stream_pass_f64(A.data_ptr(), m, n, lda, _p(w), _p(u), _p(g), _p(sc), float(sa), float(su),
+                                 zss.data_ptr(), int(flags), _p(istop), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "pla_stream_pass_f64")
+    return zss
+
+
+def matvec(A, x, alpha=1.0, y=None, beta=0.0):
+    """y <- alpha * A @ x + beta * y  (fresh y when None).  Returns (y, zss) with zss[-1] = |y|^2."""
+    A2, _ = _rowmajor(A, "A")
+    x = _vec(x, "x")
+    if y is None:
+        y = torch.zeros(A2.shape[0], dtype=F64, device=A2.device)
+        beta = 0.0
+    zss = stream_pass(A2, w=x, u=y, sa=alpha, su=beta, flags=PASS_DOT)
+    return y, zss
+
+
+def rmatvec(A, u):
+    """z = A^T u.  Returns zss (z = zss[:n], zss[n] = |u|^2)."""
+    A2, _ = _rowmajor(A, "A")
+    return stream_pass(A2, u=_vec(u, "u"), flags=PASS_AXPY)
+
+
+# ---------------------------------------------------------------------------------------- K3b
+def trsv_upper(R, b, trans=False, out=None, istop=None):
+    lib = _lib.load()
+    _req(R, "R")
+    n = R.shape[0]
+    if R.stride(1) != 1:
+        R = R.contiguous()
+    b = _vec(b, "b")
+    if out is None:
+        out = torch.empty(n, dtype=F64, device=R.device)
+    rc = lib.pla_trsv_upper_f64(R.data_ptr(), n, R.stride(0), 1 if trans else 0, b.data_ptr(), out.data_ptr(),
+                                _p(istop), _stream())
+    _lib.check(rc, "pla_trsv_upper_f64")
+    return out
+
+
+# ---------------------------------------------------------------------------------------- LSQR state
+def lsqr_init(t, zss, bsq, atol, btol, conlim, iter_lim, x0, x, v, w, dstate, istate):
+    rc = _lib.load().pla_lsqr_init_f64(x.numel(), t.data_ptr(), zss.data_ptr(), bsq.data_ptr(), float(atol),
+                                       float(btol), float(conlim), int(iter_lim), _p(x0), x.data_ptr(),
+                                       v.data_ptr(), w.data_ptr(), dstate.data_ptr(), istate.data_ptr(), _stream())
+    _lib.check(rc, "pla_lsqr_init_f64")
+
+
+def lsqr_step(t, zss, x, v, w, dstate, istate, hist):
+    rc = _lib.load().pla_lsqr_step_f64(x.numel(), t.data_ptr(), zss.data_ptr(), x.data_ptr(), v.data_ptr(),
+                                       w.data_ptr(), dstate.data_ptr(), istate.data_ptr(), hist.data_ptr(), _stream())
+    _lib.check(rc, "pla_lsqr_step_f64")
+
+
+def lsqr_ridge(sd, xw, ub, zss, sc=None, sa=1.0, su=0.0, istop=None):
+    rc = _lib.load().pla_lsqr_ridge_f64(ub.numel(), float(sd), _p(xw), ub.data_ptr(), _p(sc), float(sa), float(su),
+                                        zss.data_ptr(), _p(istop), _stream())
+    _lib.check(rc, "pla_lsqr_ridge_f64")
+
+
+def sumsq(x, out=None):
+    lib = _lib.load()
+    x = _vec(x, "x")
+    if out is None:
+        out = torch.empty(1, dtype=F64, device=x.device)
+    ws = Workspace.get(x.device, lib.pla_sumsq_workspace_bytes(x.numel()), "sumsq")
+    _lib.check(lib.pla_sumsq_f64(x.data_ptr(), x.numel(), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+               "pla_sumsq_f64")
+    return out
+
+
+# ---------------------------------------------------------------------------------------- GEMM
+def gemm(A, B, transa=False, transb=False, alpha=1.0, beta=0.0, out=None):
+    """out = alpha * op(A) @ op(B) + beta * out   (FP64 DMMA kernel)."""
+    lib = _lib.load()
+    A, lda = _rowmajor(A, "A")
+    B, ldb = _rowmajor(B, "B")
+    M, K = (A.shape[1], A.shape[0]) if transa else A.shape
+    Kb, N = (B.shape[1], B.shape[0]) if transb else B.shape
+    if K != Kb:
+        raise ValueError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=F64, device=A.device)
+        beta = 0.0
+    elif out.shape != (M, N) or out.stride(1) != 1:
+        raise ValueError("gemm: out must be a row-major (M, N) tensor")
+    _req(out, "out")
+    nb = lib.pla_gemm_workspace_bytes(M, N, K)
+    ws = Workspace.get(A.device, nb, "gemm")
+    ldc = out.stride(0) if M > 1 else max(N, 1)
+    rc = lib.pla_gemm_f64(int(transa), int(transb), M, N, K, float(alpha), A.data_ptr(), lda, B.data_ptr(), ldb,
+                          float(beta), out.data_ptr(), ldc, ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "pla_gemm_f64")
+    return out
+
+
+# ---------------------------------------------------------------------------------------- K1
+def sketch_gauss(A, d, seed, scale, out, bvec=None, col_offset=0, beta=0.0):
+    """out[:d, :n(+1)] = beta*out + scale * G(seed)[:, col_offset:col_offset+m] @ [A | bvec]."""
+    lib = _lib.load()
+    A, lda = _rowmajor(A, "A")
+    m, n = A.shape
+    nb = lib.pla_sketch_gauss_workspace_bytes(d, n, m)
+    ws = Workspace.get(A.device, nb, "gemm")
+    rc = lib.pla_sketch_gauss_f64(A.data_ptr(), m, n, lda, _p(bvec), d, ctypes.c_uint64(seed), col_offset,
+                                  float(scale), float(beta), out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel(),
+                                  _stream())
+    _lib.check(rc, "pla_sketch_gauss_f64")
+    return out
+
+
+def philox_normal_fill(rows, cols, seed, scale=1.0, row_offset=0, col_offset=0, device="cuda"):
+    out = torch.empty(rows, cols, dtype=F64, device=device)
+    rc = _lib.load().pla_philox_normal_fill_f64(out.data_ptr(), rows, cols, cols, ctypes.c_uint64(seed), row_offset,
+                                                col_offset, float(scale), _stream())
+    _lib.check(rc, "pla_philox_normal_fill_f64")
+    return out
+
+
+# ---------------------------------------------------------------------------------------- K2
+class SjltPlan:
+    """Destination-major plan of a d x m SJLT given in index form (rows[m,k] int32, signs[m,k] int8)."""
+
+    def __init__(self, rows, signs, d, validate=False):
+        lib = _lib.load()
+        _req(rows, "rows", torch.int32)
+        _req(signs, "signs", torch.int8)
+        rows, signs = rows.contiguous(), signs.contiguous()
+        self.m, self.k = rows.shape
+        self.d = int(d)
+        self.buf = torch.empty(lib.pla_sjlt_plan_bytes(self.d, self.m, self.k), dtype=torch.uint8, device=rows.device)
+        ws = Workspace.get(rows.device, lib.pla_sjlt_plan_workspace_bytes(self.d, self.m, self.k), "sjlt")
+        rc = lib.pla_sjlt_plan_f64(rows.data_ptr(), signs.data_ptr(), self.m, self.k, self.d, self.buf.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(rc, "pla_sjlt_plan_f64")
+        if validate:
+            bad = ctypes.c_int64(0)
+            _lib.check(lib.pla_sjlt_plan_status(self.buf.data_ptr(), ctypes.byref(bad)), "pla_sjlt_plan_status")
+            if bad.value:
+                raise ValueError(f"SJLT index form has {bad.value} row indices outside [0, {self.d})")
+
+    def apply(self, A, scale, out, bvec=None, out_b=None, accumulate=False):
+        lib = _lib.load()
+        A, lda = _rowmajor(A, "A")
+        m, n = A.shape
+        if m != self.m:
+            raise ValueError(f"SJLT has {self.m} columns but A has {m} rows")
+        ldob = out_b.stride(0) if (out_b is not None and out_b.numel() > 1) else 1
+        rc = lib.pla_sjlt_apply_f64(self.buf.data_ptr(), self.d, self.m, self.k, A.data_ptr(), n, lda, _p(bvec),
+                                    float(scale), out.data_ptr(), out.stride(0), _p(out_b), ldob,
+                                    1 if accumulate else 0, _stream())
+        _lib.check(rc, "pla_sjlt_apply_f64")
+        return out
+
+
+def sjlt_generate(d, m, k, seed, col_offset=0, device="cuda"):
+    rows = torch.empty(m, k, dtype=torch.int32, device=device)
+    signs = torch.empty(m, k, dtype=torch.int8, device=device)
+    rc = _lib.load().pla_sjlt_generate(d, m, k, ctypes.c_uint64(seed), col_offset, rows.data_ptr(), signs.data_ptr(),
+                                       _stream())
+    _lib.check(rc, "pla_sjlt_generate")
+    return rows, signs
+
+
+# ---------------------------------------------------------------------------------------- K3a / K6
+def geqrf(W, ncols_factor):
+    """In-place Householder QR of the leading columns of the row-major W; returns tau."""
+    lib = _lib.load()
+    _req(W, "W")
+    if W.dim() != 2 or W.stride(1) != 1:
+        raise ValueError("geqrf: W must be a row-major 2-D tensor")
+    M, N = W.shape
+    tau = torch.empty(ncols_factor, dtype=F64, device=W.device)
+    ws = Workspace.get(W.device, lib.pla_qr_workspace_bytes(M, N), "qr")
+    rc = lib.pla_geqrf_f64(W.data_ptr(), M, N, W.stride(0), ncols_factor, tau.data_ptr(), ws.data_ptr(), ws.numel(),
+                           _stream())
+    _lib.check(rc, "pla_geqrf_f64")
+    return tau
+
+
+def orgqr(W, tau, K=None):
+    lib = _lib.load()
+    M = W.shape[0]
+    K = tau.numel() if K is None else K
+    Q = torch.empty(M, K, dtype=F64, device=W.device)
+    ws = Workspace.get(W.device, lib.pla_qr_workspace_bytes(M, K), "qr")
+    rc = lib.pla_orgqr_f64(W.data_ptr(), M, K, W.stride(0), tau.data_ptr(), Q.data_ptr(), K, ws.data_ptr(),
+                           ws.numel(), _stream())
+    _lib.check(rc, "pla_orgqr_f64")
+    return Q
+
+
+def qr_economic(Y):
+    """(Q, R) of a tall row-major matrix, LAPACK sign conventions (scipy.linalg.qr(mode='economic'))."""
+    Y, _ = _rowmajor(Y, "Y")
+    W = Y.clone()
+    M, N = W.shape
+    K = min(M, N)
+    tau = geqrf(W, K)
+    Q = orgqr(W, tau, K)
+    R = torch.triu(W[:K, :])
+    return Q, R

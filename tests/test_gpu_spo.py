@@ -1,0 +1,181 @@
+"""GPU: the sketch-and-precondition driver against (1) the golden fixtures (reference outputs) with
+the reference's own sketching operator replayed, (2) the oracle run live on the same inputs, and
+(3) the mathematical properties the reference's own test-suite asserts
+(parla/tests/test_drivers/test_optim/test_overdet_least_squares.py:142-251).
+
+Stated fp64 tolerances (BASELINE.json north_star): 1e-10 relative on x and on |Ax - b|."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parla_oracle as orc
+from tests.helpers import SPO_FIXTURES, Replay, load_golden, problem_from_fixture, sjlt_from_fixture
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+TOL_X = 1e-10
+
+
+@pytest.fixture(scope="module")
+def rla():
+    import parla_b200
+    return parla_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def replayed_operator(fx, d, m):
+    if str(fx["sketch"]) == "sjlt":
+        return sjlt_from_fixture(fx, d, m)
+    return orc.gaussian_operator(d, m, np.random.default_rng(int(fx["rng_seed"])))
+
+
+@pytest.mark.parametrize("name", SPO_FIXTURES)
+def test_spo_matches_reference_fixture(rla, name):
+    fx = load_golden(name)
+    A, b = problem_from_fixture(fx)
+    m, n = A.shape
+    d = int(float(fx["sf"]) * n)
+    S = replayed_operator(fx, d, m)
+    alg = rla.SPO(Replay(S), float(fx["sf"]), str(fx["mode"]))
+    x, log = alg(dev(A), dev(b), float(fx["delta"]), float(fx["tol"]), int(fx["iter_lim"]), None)
+    x = x.cpu().numpy()
+    assert np.linalg.norm(x - fx["x"]) <= TOL_X * np.linalg.norm(fx["x"])
+    r = np.linalg.norm(A @ x - b)
+    assert abs(r - float(fx["resid_norm"])) <= TOL_X * float(fx["resid_norm"])
+    assert abs((log.errors.size - 1) - (fx["errors"].size - 1)) <= 1           # iteration count +-1
+    k = min(log.errors.size, fx["errors"].size)
+    assert np.allclose(log.errors[:k], fx["errors"][:k], rtol=1e-6, atol=1e-11 * fx["errors"][0])
+    assert log.times.size == log.errors.size and log.time_sketch > 0 and log.time_iterate > 0
+
+
+def test_spo_cfg1_full_size_parity(rla):
+    """BASELINE.json configs[0] (2^16 x 500, SJLT k=8, d=4n, tol 1e-12) against the reference's output."""
+    fx = load_golden("spo_cfg1_65536x500")
+    A, b = problem_from_fixture(fx)
+    S = sjlt_from_fixture(fx, 2000, 65536)
+    x, log = rla.SPO(Replay(S), 4, 'qr')(dev(A), dev(b), 0.0, 1e-12, 100, None)
+    x = x.cpu().numpy()
+    assert np.linalg.norm(x - fx["x"]) <= TOL_X * np.linalg.norm(fx["x"])
+    assert abs(np.linalg.norm(A @ x - b) - float(fx["resid_norm"])) <= TOL_X * float(fx["resid_norm"])
+    assert abs(log.errors.size - fx["errors"].size) <= 1
+    assert log.passes_over_A <= log.iters + 4            # sketch + presolve/init + iterations + final
+
+
+@pytest.mark.parametrize("mode", ["qr", "svd", "chol"])
+@pytest.mark.parametrize("delta", [0.0, 0.5])
+def test_spo_against_live_oracle(rla, mode, delta):
+    rng = np.random.default_rng(100)
+    m, n = 3000, 120
+    A = rng.standard_normal((m, n)) * np.logspace(0, 3, n)
+    b = A @ rng.standard_normal(n) + rng.standard_normal(m)
+    S = orc.sjlt_operator(4 * n, m, np.random.default_rng(3), 8)
+    x_ref, log_ref = orc.SPO(Replay(S), 4, mode)(A, b, delta, 1e-12, 100, None)
+    x, log = rla.SPO(Replay(S), 4, mode)(dev(A), dev(b), delta, 1e-12, 100, None)
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) <= TOL_X * np.linalg.norm(x_ref)
+    assert abs(log.errors.size - log_ref.errors.size) <= 1
+    assert abs(log.errors[0] - log_ref.errors[0]) <= 1e-9 * log_ref.errors[0]
+
+
+def test_spo_host_buffers_in_numpy_out(rla):
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((2000, 60)); b = rng.standard_normal(2000)
+    x, log = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(A, b, 0.0, 1e-12, 100, 3)
+    assert isinstance(x, np.ndarray)
+    x_opt = np.linalg.lstsq(A, b, rcond=None)[0]
+    assert np.linalg.norm(x - x_opt) <= 1e-9 * np.linalg.norm(x_opt)
+
+
+@pytest.mark.parametrize("gen_name", ["SkOpSJ", "SkOpGA", "sjlt_operator", "gaussian_operator"])
+@pytest.mark.parametrize("mode", ["qr", "svd"])
+def test_native_operators_convergence_rate(rla, gen_name, mode):
+    """Reference property test (test_overdet_least_squares.py:234-251): log-linear convergence with
+    R^2 >= 0.95, slope < -0.3, final error <= 1e-6 -- with the Philox-native operators."""
+    rng = np.random.default_rng(897809809)
+    m, n = 1000, 100
+    spec = np.concatenate([1e5 + rng.random(30), 1 + rng.random(70)])
+    U = orc.orthonormal_operator(m, n, rng)
+    Vt = orc.orthonormal_operator(n, n, rng)
+    A = (U * spec) @ Vt
+    xt = np.concatenate([rng.standard_normal(30) / 1e5, rng.standard_normal(70)])
+    b_orth = rng.standard_normal(m) * 1e2
+    b_orth -= U @ (U.T @ b_orth)
+    b = A @ xt + b_orth
+    gen = getattr(rla, gen_name)
+    gen = gen(8) if gen_name == "SkOpSJ" else (gen() if gen_name == "SkOpGA" else gen)
+    x, log = rla.SPO(gen, 3, mode)(dev(A), dev(b), 0.0, 1e-12, 100, np.random.default_rng(34998751340))
+    errs = log.errors[1:]
+    t = np.arange(errs.size)
+    slope, icpt = np.polyfit(t, np.log(errs), 1)
+    fit = slope * t + icpt
+    r2 = 1 - np.sum((np.log(errs) - fit) ** 2) / np.sum((np.log(errs) - np.log(errs).mean()) ** 2)
+    assert r2 >= 0.95 and slope < -0.3 and log.errors[-1] <= 1e-6
+    x = x.cpu().numpy()
+    res = A @ x - b                                               # test_residual_proj, :171-180
+    assert np.linalg.norm(U @ (U.T @ res)) / np.linalg.norm(res) <= 1e-6
+    assert abs(np.linalg.norm(Vt @ x) - np.linalg.norm(Vt @ xt)) <= 1e-6 * (1 + np.linalg.norm(Vt @ xt))
+
+
+def test_spo_edge_cases(rla):
+    rng = np.random.default_rng(1)
+    # consistent system: presolve is (nearly) exact, LSQR stops immediately or after a step
+    A = rng.standard_normal((500, 20)); xt = rng.standard_normal(20)
+    x, log = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(dev(A), dev(A @ xt), 0.0, 1e-12, 50, 1)
+    assert np.linalg.norm(x.cpu().numpy() - xt) <= 1e-10 * np.linalg.norm(xt)
+    # b orthogonal to range(A): x = 0, zero vector beats the presolve (rel_err >= 1 branch)
+    Q = np.linalg.qr(rng.standard_normal((500, 21)))[0]
+    x, log = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(dev(Q[:, :20]), dev(Q[:, 20]), 0.0, 1e-12, 50, 1)
+    assert np.linalg.norm(x.cpu().numpy()) <= 1e-10
+    # d clipped to m with a warning (dim_checks), square-ish problem
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        A = rng.standard_normal((60, 50)); b = rng.standard_normal(60)
+        x, _ = rla.SPO(rla.SkOpGA(), 4, 'qr')(dev(A), dev(b), 0.0, 1e-12, 200, 1)
+        assert any("embedding dimension" in str(i.message) for i in w)
+    assert np.linalg.norm(x.cpu().numpy() - np.linalg.lstsq(A, b, rcond=None)[0]) <= 1e-8
+    with pytest.raises(ValueError):
+        rla.SPO(rla.SkOpSJ(8), 4, 'nope')(dev(A), dev(b), 0.0, 1e-12, 10, 1)
+    # iteration limit reached: istop 7 after exactly iter_lim steps
+    A = rng.standard_normal((2000, 100)) * np.logspace(0, 6, 100); b = rng.standard_normal(2000)
+    x, log = rla.SPO(rla.SkOpSJ(8), 1.2, 'qr')(dev(A), dev(b), 0.0, 1e-15, 5, 1)
+    assert log.errors.size - 1 == 5
+
+
+def test_sso1_sketch_and_solve(rla):
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((4000, 50)); b = A @ rng.standard_normal(50) + 0.01 * rng.standard_normal(4000)
+    S = orc.sjlt_operator(300, 4000, np.random.default_rng(5), 8)
+    x_ref, _ = orc.SSO1(Replay(S), 6)(A, b, 0.0, np.nan, 1, None)
+    x, log = rla.SSO1(Replay(S), 6)(dev(A), dev(b), 0.0, np.nan, 1, None)
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) <= 1e-10 * np.linalg.norm(x_ref)
+    assert set(log) == {"time_sketch", "time_solve"}
+    x_ref, _ = orc.SSO1(Replay(S), 6)(A, b, 0.3, np.nan, 1, None)
+    x, _ = rla.SSO1(Replay(S), 6)(dev(A), dev(b), 0.3, np.nan, 1, None)
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) <= 1e-10 * np.linalg.norm(x_ref)
+
+
+def test_spo_full_size_properties(rla):
+    """BASELINE.json configs[1] shape (2^22 x 2048 fp64, d = 4n, SJLT) through size-independent
+    properties: b = A x0 + noise  =>  the normal-equation residual is at round-off level relative to
+    |A||r|, x is within the noise cone of x0, and the error history decays linearly."""
+    free, _ = torch.cuda.mem_get_info()
+    m, n = (1 << 22, 2048) if free > 100e9 else (1 << 19, 2048)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    x0 = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    from parla_b200 import kernels as K
+    b, _ = K.matvec(A, x0)
+    b += 0.1 * torch.randn(m, dtype=torch.float64, device="cuda", generator=g)
+    x, log = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(A, b, 0.0, 1e-12, 100, 3)
+    r, zss = K.matvec(A, x, alpha=1.0, y=b.clone(), beta=-1.0)          # r = A x - b
+    atr = K.rmatvec(A, r)
+    rn = float(torch.sqrt(atr[n]))
+    assert abs(rn / (0.1 * np.sqrt(m)) - 1) < 0.01                       # |r| ~ noise level
+    assert float(torch.linalg.vector_norm(atr[:n])) <= 1e-9 * np.sqrt(m) * rn
+    assert float(torch.linalg.vector_norm(x - x0)) <= 10 * 0.1 * np.sqrt(n / m) * np.sqrt(n)
+    assert 20 <= log.iters <= 60 and log.errors[-1] <= 1e-9 * log.errors[0]
+    assert log.passes_over_A <= log.iters + 4

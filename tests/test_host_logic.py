@@ -1,0 +1,112 @@
+"""CPU: host-side logic of the drivers (no kernels), and the world_size-2 gloo path of the
+row-sharding helpers."""
+import os
+import socket
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import parla_b200 as rla
+from parla_b200.comps.determiter.logging import SketchAndPrecondLog
+from parla_b200.drivers.least_squares import dim_checks
+from parla_b200.parallel import RowSharded, allreduce_, unwrap
+
+
+def test_dim_checks_matches_reference_semantics():
+    assert dim_checks(4, 1000, 50) == 200
+    assert dim_checks(3.3, 1531, 77) == int(3.3 * 77)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert dim_checks(30, 100, 10) == 100          # clipped to n_rows, with a warning
+        assert len(w) == 1
+    with pytest.raises(AssertionError):
+        dim_checks(4, 10, 50)                          # not tall
+
+
+def test_log_wrap_up_layout():
+    log = SketchAndPrecondLog()
+    log.time_sketch, log.time_factor, log.time_presolve, log.time_iterate = 1.0, 2.0, 0.5, 4.0
+    log.wrap_up(np.array([3.0, 2.0, 1.0]), 10.0)
+    assert np.allclose(log.errors, [10.0, 3.0, 2.0, 1.0])
+    assert np.allclose(log.times, [3.0, 3.5, 5.5, 7.5])
+    log.wrap_up(np.float64(0.0), 1.0)                  # early-exit path hands a scalar
+    assert log.errors.shape == (2,)
+
+
+def test_public_names_and_exec_alias():
+    for name in ("SPO", "SSO1", "SkOpGA", "SkOpSJ", "RS1", "RF1", "QB1", "QB2", "SVD1", "EVD1",
+                 "gaussian_operator", "sjlt_operator", "RowSketcher", "RangeFinder", "QBDecomposer",
+                 "OverLstsqSolver", "SVDecomposer", "EVDecomposer", "SketchAndPrecondLog"):
+        assert hasattr(rla, name)
+    for cls in (rla.SPO, rla.SSO1, rla.RS1, rla.RF1, rla.QB1, rla.QB2, rla.SVD1, rla.EVD1, rla.SkOpGA, rla.SkOpSJ):
+        assert cls.exec is cls.__call__
+    alg = rla.SPO(rla.SkOpSJ(8), 4, mode='qr')
+    assert alg.mode == 'qr' and alg.sampling_factor == 4 and isinstance(alg.iterative_solver, rla.PcSS2)
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused loudly, never routed to a host implementation."""
+    from parla_b200 import kernels as K
+    with pytest.raises(TypeError):
+        K.gemm(torch.zeros(4, 4, dtype=torch.float64), torch.zeros(4, 4, dtype=torch.float64))
+    with pytest.raises(TypeError):
+        K.stream_pass(torch.zeros(8, 4, dtype=torch.float64), u=torch.zeros(8, dtype=torch.float64), flags=2)
+
+
+def test_unknown_mode_raises_value_error_signature():
+    import inspect
+    sig = inspect.signature(rla.SPO.__call__)
+    assert list(sig.parameters)[1:] == ["A", "b", "delta", "tol", "iter_lim", "rng", "logging"]
+    sig = inspect.signature(rla.QB2.__init__)
+    assert list(sig.parameters)[1:] == ["rf", "blk", "overwrite_a"]
+    sig = inspect.signature(rla.RS1.__init__)
+    assert list(sig.parameters)[1:] == ["sketch_op_gen", "num_pass", "stabilizer", "passes_per_stab"]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m_local, n = 5, 3
+        rng = np.random.default_rng(0)
+        A = rng.standard_normal((world * m_local, n))
+        u = rng.standard_normal(world * m_local)
+        mine = slice(rank * m_local, (rank + 1) * m_local)
+        shard = RowSharded.from_rank(torch.from_numpy(A[mine].copy()))
+        assert shard.shape == (world * m_local, n) and shard.row_offset == rank * m_local
+        local, off, group = unwrap(shard)
+        # the per-iteration collective: partial [A^T u | |u|^2] summed over ranks
+        part = torch.cat([local.T @ torch.from_numpy(u[mine]), torch.tensor([float(u[mine] @ u[mine])], dtype=torch.float64)])
+        allreduce_(part, group)
+        want = np.concatenate([A.T @ u, [u @ u]])
+        ok = np.allclose(part.numpy(), want, rtol=1e-13)
+        # a non-sharded tensor is passed through untouched
+        t = torch.ones(2, dtype=torch.float64)
+        allreduce_(t, unwrap(t)[2])
+        ok = ok and torch.equal(t, torch.ones(2, dtype=torch.float64))
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_allreduce_gloo_world2():
+    world = 2
+    out = mp.get_context("spawn").Array("i", [0] * world)
+    procs = [mp.get_context("spawn").Process(target=_worker, args=(r, world, port_, out))
+             for port_ in [_free_port()] for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(out) == [1, 1]
