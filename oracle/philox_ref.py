@@ -84,7 +84,7 @@ def sjlt_columns(d, m, k, seed, col_offset=0):
     rows = np.empty((m, k), dtype=np.int32)
     signs = np.empty((m, k), dtype=np.int8)
     gi = np.arange(col_offset, col_offset + m, dtype=np.uint64)
-    ncalls = 4                                        # enough words for k <= 8 plus a few redraws
+    ncalls = 24                                       # plenty of words for redraws even when d ~ k
     words = []
     for call in range(ncalls):
         ctr = np.zeros((m, 4), dtype=np.uint32)

@@ -44,9 +44,37 @@ __global__ void __launch_bounds__(256) sumsq_stage2(const double* part, int nb, 
     if (threadIdx.x == 0) out[0] = acc;
 }
 
+// ------------------------------------------------------------------ FP64 tensor pipe probe (measurement hook)
+__global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double* sink) {
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c[2 * i], c[2 * i + 1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    if (s == 123.456) sink[0] = s;
+}
+
 }  // namespace pla
 
 using namespace pla;
+
+// Runs `iters` x 8 independent DMMA.8x8x4 per warp on every SM (8 warps x `ctas_per_sm` CTAs).
+// flops = 2 * 256 * 8 * iters * (8 warps) * grid.  Timing is the caller's (CUDA events).
+extern "C" int pla_dmma_probe(int iters, int ctas_per_sm, double* sink, void* stream) {
+    PLA_CHECK_ARG(iters >= 1, 1, "iters < 1");
+    PLA_CHECK_ARG(ctas_per_sm >= 1 && ctas_per_sm <= 8, 2, "ctas_per_sm out of range");
+    PLA_CHECK_ARG(sink != nullptr, 3, "sink is null");
+    dmma_probe_kernel<<<num_sms() * ctas_per_sm, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
 
 extern "C" int pla_version(void) { return 100; }
 extern "C" const char* pla_last_error(void) { return g_err; }

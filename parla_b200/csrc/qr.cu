@@ -36,6 +36,7 @@ struct PanelParams {
     int jb;                 // panel width (<= 16)
     double* tau;            // tau + j0
     double* gpart;          // [2][grid][QR_NP]
+    double* drowbuf;        // [2][QR_NB]: snapshot of the diagonal row of the current column step
     unsigned int* counter;  // zeroed before launch
     long long rows_per_cta;
 };
@@ -56,6 +57,14 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(const PanelParams 
 #pragma unroll
     for (int c = 0; c < QR_NP; ++c) part[c] = 0.0;
     for (long long i = r_begin + tid; i < r_end; i += QR_THREADS) {
+        if (i == p.j0) {
+            // The diagonal row of step j is rewritten by its owner DURING step j, so every other
+            // thread must read a snapshot taken before the barrier, never the matrix itself.
+            const double* row = Ap + i * p.lda;
+#pragma unroll
+            for (int c = 0; c < QR_NB; ++c)
+                if (c < jb) p.drowbuf[c] = row[c];
+        }
         if (i > p.j0) {
             const double* row = Ap + i * p.lda;
             const double x = row[0];
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(const PanelParams 
 
         // ---- reflector j (LAPACK dlarfg): beta = -sign(alpha)|x|, tau = (beta-alpha)/beta, v = x/(alpha-beta)
         const long long dj = p.j0 + j;
-        const double* drow = Ap + dj * p.lda;
+        const double* drow = p.drowbuf + (j & 1) * QR_NB;
         const double alpha = __ldcg(drow + j);
         const double sigma = red[0];
         double beta = alpha, tau = 0.0, scale = 0.0;
@@ -129,6 +138,12 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(const PanelParams 
                 for (int c = 0; c < QR_NB; ++c) {
                     a[c] = 0.0;
                     if (c > j && c < jb) { a[c] = fma(-v, wv[c], row[c]); row[c] = a[c]; }
+                }
+                if (i == dj + 1 && j + 1 < jb) {          // next step's diagonal row: publish its snapshot
+                    double* nxt = p.drowbuf + ((j + 1) & 1) * QR_NB;
+#pragma unroll
+                    for (int c = 0; c < QR_NB; ++c)
+                        if (c > j && c < jb) nxt[c] = a[c];
                 }
                 if (i > dj + 1 && j + 1 < jb) {
                     double x = 0.0;
@@ -234,14 +249,19 @@ __global__ void __launch_bounds__(QR_THREADS) qr_trail_w_kernel(const TrailParam
         __syncthreads();
         if (c < p.nc) {
             const int lim = (int)min((long long)QR_TR, r_end - row0);
-            for (int r = 0; r < lim; ++r) {
-                const double x = p.C[(row0 + r) * p.ldc + c];
-                const double2* v2 = reinterpret_cast<const double2*>(vt[r]);
+            for (int r = 0; r < lim; r += 8) {
+                double x[8];
 #pragma unroll
-                for (int k = 0; k < QR_NB / 2; ++k) {
-                    const double2 vv = v2[k];
-                    acc[2 * k] = fma(vv.x, x, acc[2 * k]);
-                    acc[2 * k + 1] = fma(vv.y, x, acc[2 * k + 1]);
+                for (int q = 0; q < 8; ++q) x[q] = (r + q < lim) ? p.C[(row0 + r + q) * p.ldc + c] : 0.0;   // 8 loads in flight
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double2* v2 = reinterpret_cast<const double2*>(vt[r + q]);
+#pragma unroll
+                    for (int k = 0; k < QR_NB / 2; ++k) {
+                        const double2 vv = v2[k];
+                        acc[2 * k] = fma(vv.x, x[q], acc[2 * k]);
+                        acc[2 * k + 1] = fma(vv.y, x[q], acc[2 * k + 1]);
+                    }
                 }
             }
         }
@@ -283,17 +303,22 @@ __global__ void __launch_bounds__(QR_THREADS) qr_trail_apply_kernel(const TrailP
         __syncthreads();
         if (c < p.nc) {
             const int lim = (int)min((long long)QR_TR, r_end - row0);
-            for (int r = 0; r < lim; ++r) {
-                double* dst = p.C + (row0 + r) * p.ldc + c;
-                const double2* v2 = reinterpret_cast<const double2*>(vt[r]);
-                double s = 0.0;
+            for (int r = 0; r < lim; r += 8) {
+                double x[8];
 #pragma unroll
-                for (int k = 0; k < QR_NB / 2; ++k) {
-                    const double2 vv = v2[k];
-                    s = fma(vv.x, w2[2 * k], s);
-                    s = fma(vv.y, w2[2 * k + 1], s);
+                for (int q = 0; q < 8; ++q) x[q] = (r + q < lim) ? p.C[(row0 + r + q) * p.ldc + c] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double2* v2 = reinterpret_cast<const double2*>(vt[r + q]);
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < QR_NB / 2; ++k) {
+                        const double2 vv = v2[k];
+                        s = fma(vv.x, w2[2 * k], s);
+                        s = fma(vv.y, w2[2 * k + 1], s);
+                    }
+                    if (r + q < lim) p.C[(row0 + r + q) * p.ldc + c] = x[q] - s;
                 }
-                *dst -= s;
             }
         }
     }
@@ -312,6 +337,7 @@ __global__ void __launch_bounds__(256) qr_eye_kernel(double* Q, long long M, lon
 struct QrWs {
     unsigned int* counter;   // 64 B
     double* gpart;           // panel partials: 2 * sms * QR_NP
+    double* drowbuf;         // 2 * QR_NB
     double* gram;            // sms * 256
     double* T;               // 256
     double* wpart;           // splits * 16 * ncols
@@ -324,9 +350,10 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_counter = take(256);
     const size_t o_gpart = take((size_t)2 * sms * QR_NP * 8);
+    const size_t o_drow = take((size_t)2 * QR_NB * 8);
     const size_t o_gram = take((size_t)sms * QR_NB * QR_NB * 8);
     const size_t o_T = take(QR_NB * QR_NB * 8);
-    int max_splits = (int)((M + 1023) / 1024);
+    int max_splits = (int)((M + 255) / 256);
     if (max_splits > 2 * sms) max_splits = 2 * sms;
     if (max_splits < 1) max_splits = 1;
     const size_t o_w = take((size_t)max_splits * QR_NB * (size_t)(N > 0 ? N : 1) * 8);
@@ -334,6 +361,7 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
         char* b = (char*)base;
         out->counter = (unsigned int*)(b + o_counter);
         out->gpart = (double*)(b + o_gpart);
+        out->drowbuf = (double*)(b + o_drow);
         out->gram = (double*)(b + o_gram);
         out->T = (double*)(b + o_T);
         out->wpart = (double*)(b + o_w);
@@ -351,7 +379,7 @@ static int run_panel(double* A, long long lda, long long M, long long j0, int jb
     if (G < 1) G = 1;
     PanelParams pp;
     pp.A = A; pp.lda = lda; pp.M = M; pp.j0 = j0; pp.jb = jb; pp.tau = tau + j0; pp.gpart = w.gpart;
-    pp.counter = w.counter; pp.rows_per_cta = (rows + G - 1) / G;
+    pp.drowbuf = w.drowbuf; pp.counter = w.counter; pp.rows_per_cta = (rows + G - 1) / G;
     PLA_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st));
     void* args[] = {(void*)&pp};
     PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));

@@ -13,10 +13,15 @@
 
 namespace pla {
 
-constexpr int SP_CONS = 256;          // consumer threads (8 warps)
-constexpr int SP_THREADS = SP_CONS + 32;
+constexpr int SP_GROUP = 256;         // consumer threads per group (8 warps)
 constexpr int SP_RMAX = 8;            // max rows per tile
 constexpr int SP_MAX_STAGES = 8;
+constexpr int SP_MAX_GROUPS = 2;
+
+// rows per tile as a function of the column-ownership shape: ~32 KB tiles, R*n even for odd n
+template <int VEC, int J> struct SpRows {
+    static constexpr int value = VEC == 2 ? (J >= 8 ? 1 : 8 / J) : (J <= 2 ? 8 : (J == 4 ? 4 : 2));
+};
 
 struct StreamPassParams {
     const double* A;
@@ -26,33 +31,38 @@ struct StreamPassParams {
     const double* g;
     const double* sc;       // device {sa, su} or null
     double sa, su;
-    double* zpart;          // [grid][n]
-    double* sspart;         // [grid]
+    double* zpart;          // [grid * groups][n]
+    double* sspart;         // [grid * groups]
     const int* istop;
     int flags;
-    int R;                  // rows per tile
     int stages;
     int use_tma;            // 1: contiguous + 16B aligned rows tiles
     long long ntiles;
 };
 
-template <int VEC, int J>
-__global__ void __launch_bounds__(SP_THREADS, 1) stream_pass_kernel(const StreamPassParams p) {
+// NG independent consumer groups per CTA take alternate tiles of the CTA's sequence, so the
+// dot -> reduce -> barrier -> axpy latency chain of one tile overlaps with the other group's.
+template <int VEC, int J, int NG>
+__global__ void __launch_bounds__(NG * SP_GROUP + 32, 1) stream_pass_kernel(const StreamPassParams p) {
     if (p.istop != nullptr && *p.istop != 0) return;
+    constexpr int RT = SpRows<VEC, J>::value;
+    constexpr int NCONS = NG * SP_GROUP;
+    constexpr int NW = SP_GROUP / 32;
     extern __shared__ __align__(128) unsigned char sp_smem[];
     const int tid = threadIdx.x;
     const long long n = p.n;
-    const int R = p.R;
     const int S = p.stages;
-    const size_t stage_elems = (size_t)R * n;
+    const size_t stage_elems = (size_t)RT * n;
     double* tiles = reinterpret_cast<double*>(sp_smem);
     size_t off = ((size_t)S * stage_elems * 8 + 15) & ~(size_t)15;
     uint64_t* full = reinterpret_cast<uint64_t*>(sp_smem + off);
     uint64_t* empty = full + SP_MAX_STAGES;
-    double* red = reinterpret_cast<double*>(empty + SP_MAX_STAGES);     // [2][8 warps][RMAX]
+    double* red = reinterpret_cast<double*>(empty + SP_MAX_STAGES);     // [groups][2][8 warps][RMAX]
+    double* ustage = red + SP_MAX_GROUPS * 2 * NW * SP_RMAX;            // [stages][RMAX]  old u of the tile rows
+    double* gstage = ustage + SP_MAX_STAGES * SP_RMAX;                  // [stages][RMAX]  g of the tile rows
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], SP_CONS / 32); }
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1 + 32); mbar_init(&empty[s], NW); }
         fence_mbar_init();
     }
     __syncthreads();
@@ -61,17 +71,23 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_pass_kernel(const Stream
     const bool do_axpy = (p.flags & PLA_PASS_AXPY) != 0;
     const bool axpy_g = (p.flags & PLA_PASS_AXPY_G) != 0;
 
-    if (tid >= SP_CONS) {
+    if (tid >= NCONS) {
         // ------------------------------------------------------------- producer warp
-        const int lane = tid - SP_CONS;
+        const int lane = tid - NCONS;
         const uint64_t pol = l2_policy_evict_first();
         int s = 0; uint32_t ph = 0;
         for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-            const long long r0 = t * R;
-            const int rows = (int)min((long long)R, p.m - r0);
+            const long long r0 = t * RT;
+            const int rows = (int)min((long long)RT, p.m - r0);
             const size_t elems = (size_t)rows * n;
             if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
             __syncwarp();
+            // per-row scalars (old u, g) ride the same pipeline: their HBM latency is hidden by the ring
+            if (lane < rows) {
+                if (p.u != nullptr) cp_async8(ustage + s * SP_RMAX + lane, p.u + r0 + lane, true);
+                if (axpy_g) cp_async8(gstage + s * SP_RMAX + lane, p.g + r0 + lane, true);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
             double* dst = tiles + (size_t)s * stage_elems;
             const bool tma_ok = p.use_tma && ((elems & 1) == 0);
             if (tma_ok) {
@@ -94,49 +110,54 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_pass_kernel(const Stream
     }
 
     // ----------------------------------------------------------------- consumer warps
-    const int lane = tid & 31, wid = tid >> 5;
+    const int grp = tid / SP_GROUP, gt = tid % SP_GROUP;     // group, thread within group
+    const int lane = gt & 31, wid = gt >> 5;
     double sa = p.sa, su = p.su;
     if (p.sc != nullptr) { sa = p.sc[0]; su = p.sc[1]; }
 
-    // column ownership: VEC consecutive columns at c0(j) = VEC * (tid + SP_CONS * j)
+    // column ownership: VEC consecutive columns at c0(j) = VEC * (gt + SP_GROUP * j)
     double wreg[J * VEC], zacc[J * VEC];
 #pragma unroll
     for (int j = 0; j < J; ++j)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const long long c = (long long)VEC * (tid + SP_CONS * j) + v;
+            const long long c = (long long)VEC * (gt + SP_GROUP * j) + v;
             wreg[j * VEC + v] = (do_dot && c < n) ? p.w[c] : 0.0;
             zacc[j * VEC + v] = 0.0;
         }
-    double ss = 0.0;     // thread r (< RMAX) accumulates u_r^2 over its tiles
+    double ss = 0.0;     // thread r (< RT) of each group accumulates u_r^2 over its tiles
+    double* gred = red + (size_t)grp * 2 * NW * SP_RMAX;
 
-    int s = 0; uint32_t ph = 0; int flip = 0;
-    for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const long long r0 = t * R;
-        const int rows = (int)min((long long)R, p.m - r0);
-        // prefetch the per-row scalars of this tile (broadcast loads) before blocking on the tile
-        double uo[SP_RMAX], gq[SP_RMAX];
-#pragma unroll
-        for (int r = 0; r < SP_RMAX; ++r) {
-            uo[r] = (r < rows && p.u != nullptr) ? p.u[r0 + r] : 0.0;
-            gq[r] = (r < rows && axpy_g) ? p.g[r0 + r] : 0.0;
-        }
+    // this group consumes tiles q = grp, grp + NG, ... of the CTA's sequence; tile q lives in stage q % S
+    int flip = 0;
+    long long q = grp;
+    for (long long t = blockIdx.x + (long long)grp * gridDim.x; t < p.ntiles; t += (long long)NG * gridDim.x, q += NG) {
+        const int s = (int)(q % S);
+        const uint32_t ph = (uint32_t)((q / S) & 1);
+        const long long r0 = t * RT;
+        const int rows = (int)min((long long)RT, p.m - r0);
         mbar_wait(&full[s], ph);
         const double* tile = tiles + (size_t)s * stage_elems;
+        double uo[RT], gq[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            uo[r] = (r < rows && p.u != nullptr) ? ustage[s * SP_RMAX + r] : 0.0;
+            gq[r] = (r < rows && axpy_g) ? gstage[s * SP_RMAX + r] : 0.0;
+        }
 
-        double unew[SP_RMAX];
+        double unew[RT];
         if (do_dot) {
-            double dot[SP_RMAX];
+            double dot[RT];
 #pragma unroll
-            for (int r = 0; r < SP_RMAX; ++r) dot[r] = 0.0;
+            for (int r = 0; r < RT; ++r) dot[r] = 0.0;
 #pragma unroll
-            for (int r = 0; r < SP_RMAX; ++r) {
-                if (r < rows) {
-                    const double* row = tile + (size_t)r * n;
+            for (int j = 0; j < J; ++j) {
+                const long long c = (long long)VEC * (gt + SP_GROUP * j);
+                if (c < n) {
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        const long long c = (long long)VEC * (tid + SP_CONS * j);
-                        if (c < n) {
+                    for (int r = 0; r < RT; ++r) {
+                        if (r < rows) {
+                            const double* row = tile + (size_t)r * n;
                             if (VEC == 2) {
                                 const double2 a = *reinterpret_cast<const double2*>(row + c);
                                 dot[r] = fma(a.x, wreg[j * VEC], dot[r]);
@@ -148,60 +169,60 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_pass_kernel(const Stream
                     }
                 }
             }
-            double* myred = red + (size_t)flip * (SP_CONS / 32) * SP_RMAX;
+            // all rows reduced together: RT independent shuffle chains in flight
 #pragma unroll
-            for (int r = 0; r < SP_RMAX; ++r) {
-                if (r < rows) {
-                    const double v = warp_sum(dot[r]);
-                    if (lane == 0) myred[wid * SP_RMAX + r] = v;
-                }
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int r = 0; r < RT; ++r) dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+            double* myred = gred + (size_t)flip * NW * SP_RMAX;
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < RT; ++r) myred[wid * SP_RMAX + r] = dot[r];
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(SP_CONS) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(SP_GROUP) : "memory");
 #pragma unroll
-            for (int r = 0; r < SP_RMAX; ++r) {
+            for (int r = 0; r < RT; ++r) {
                 double tot = 0.0;
-                if (r < rows) {
 #pragma unroll
-                    for (int q = 0; q < SP_CONS / 32; ++q) tot += myred[q * SP_RMAX + r];
-                }
+                for (int k = 0; k < NW; ++k) tot += myred[k * SP_RMAX + r];
                 unew[r] = fma(sa, tot, su * uo[r]);
             }
             flip ^= 1;
-            if (tid < rows) {
+            if (gt < rows) {
                 // thread r owns row r of the tile
                 double mine = 0.0;
 #pragma unroll
-                for (int r = 0; r < SP_RMAX; ++r) if (r == tid) mine = unew[r];
-                p.u[r0 + tid] = mine;
+                for (int r = 0; r < RT; ++r) if (r == gt) mine = unew[r];
+                p.u[r0 + gt] = mine;
                 ss = fma(mine, mine, ss);
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < SP_RMAX; ++r) unew[r] = uo[r];
-            if (tid < rows) {
+            for (int r = 0; r < RT; ++r) unew[r] = uo[r];
+            if (gt < rows) {
                 double mine = 0.0;
 #pragma unroll
-                for (int r = 0; r < SP_RMAX; ++r) if (r == tid) mine = unew[r];
+                for (int r = 0; r < RT; ++r) if (r == gt) mine = unew[r];
                 ss = fma(mine, mine, ss);
             }
         }
 
         if (do_axpy) {
 #pragma unroll
-            for (int r = 0; r < SP_RMAX; ++r) {
-                if (r < rows) {
-                    const double q = axpy_g ? gq[r] : unew[r];
-                    const double* row = tile + (size_t)r * n;
+            for (int j = 0; j < J; ++j) {
+                const long long c = (long long)VEC * (gt + SP_GROUP * j);
+                if (c < n) {
 #pragma unroll
-                    for (int j = 0; j < J; ++j) {
-                        const long long c = (long long)VEC * (tid + SP_CONS * j);
-                        if (c < n) {
+                    for (int r = 0; r < RT; ++r) {
+                        if (r < rows) {
+                            const double qv = axpy_g ? gq[r] : unew[r];
+                            const double* row = tile + (size_t)r * n;
                             if (VEC == 2) {
                                 const double2 a = *reinterpret_cast<const double2*>(row + c);
-                                zacc[j * VEC] = fma(a.x, q, zacc[j * VEC]);
-                                zacc[j * VEC + VEC - 1] = fma(a.y, q, zacc[j * VEC + VEC - 1]);
+                                zacc[j * VEC] = fma(a.x, qv, zacc[j * VEC]);
+                                zacc[j * VEC + VEC - 1] = fma(a.y, qv, zacc[j * VEC + VEC - 1]);
                             } else {
-                                zacc[j * VEC] = fma(row[c], q, zacc[j * VEC]);
+                                zacc[j * VEC] = fma(row[c], qv, zacc[j * VEC]);
                             }
                         }
                     }
@@ -210,23 +231,23 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stream_pass_kernel(const Stream
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (++s == S) { s = 0; ph ^= 1; }
     }
 
-    // ----------------------------------------------------------------- per-CTA partial results
+    // ----------------------------------------------------------------- per-(CTA, group) partial results
+    const size_t pidx = (size_t)blockIdx.x * NG + grp;
     if (do_axpy) {
-        double* zp = p.zpart + (size_t)blockIdx.x * n;
+        double* zp = p.zpart + pidx * n;
 #pragma unroll
         for (int j = 0; j < J; ++j)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const long long c = (long long)VEC * (tid + SP_CONS * j) + v;
+                const long long c = (long long)VEC * (gt + SP_GROUP * j) + v;
                 if (c < n) zp[c] = zacc[j * VEC + v];
             }
     }
     if (wid == 0) {
-        const double tot = warp_sum(ss);     // only lanes < RMAX hold non-zero
-        if (lane == 0) p.sspart[blockIdx.x] = tot;
+        const double tot = warp_sum(ss);     // only lanes < RT hold non-zero
+        if (lane == 0) p.sspart[pidx] = tot;
     }
 }
 
@@ -250,29 +271,35 @@ __global__ void __launch_bounds__(256) stream_pass_reduce_kernel(const double* _
     }
 }
 
-static int pick_tile_rows(long long n, size_t tile_bytes_target) {
-    long long R = (long long)(tile_bytes_target / (size_t)(8 * n));
-    if (R < 1) R = 1;
-    if (R > SP_RMAX) R = SP_RMAX;
-    if ((n & 1) && (R & 1)) R = (R < SP_RMAX) ? R + 1 : R - 1;   // keep R*n even -> 16-byte tiles
-    return (int)R;
-}
-
-template <int VEC, int J>
-static cudaError_t launch_pass(const StreamPassParams& p, int grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(stream_pass_kernel<VEC, J>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int VEC, int J, int NG>
+static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts) {
+    constexpr int RT = SpRows<VEC, J>::value;
+    const size_t stage_bytes = (size_t)RT * p.n * 8;
+    const size_t budget = 200 * 1024;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > SP_MAX_STAGES) stages = SP_MAX_STAGES;
+    if (stages < 2) return cudaErrorInvalidValue;
+    p.stages = stages;
+    p.ntiles = (p.m + RT - 1) / RT;
+    p.use_tma = (p.lda == p.n) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (((size_t)RT * p.n) % 2 == 0);
+    int grid = num_sms();
+    if ((long long)grid > p.ntiles) grid = (int)p.ntiles;
+    *nparts = grid * NG;
+    const size_t smem = (((size_t)stages * stage_bytes + 15) & ~(size_t)15) + 2 * SP_MAX_STAGES * 8 +
+                        SP_MAX_GROUPS * 2 * (SP_GROUP / 32) * SP_RMAX * 8 + 2 * SP_MAX_STAGES * SP_RMAX * 8;
+    cudaError_t e = cudaFuncSetAttribute(stream_pass_kernel<VEC, J, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    stream_pass_kernel<VEC, J><<<grid, SP_THREADS, smem, st>>>(p);
+    stream_pass_kernel<VEC, J, NG><<<grid, NG * SP_GROUP + 32, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-static size_t sp_tile_bytes_target() {
-    static size_t v = 0;
+static int sp_groups() {
+    static int v = 0;
     if (v == 0) {
-        const char* e = getenv("PLA_PASS_TILE_BYTES");
-        v = e ? (size_t)atoll(e) : (size_t)32768;
-        if (v < 1024) v = 1024;
+        const char* e = getenv("PLA_PASS_GROUPS");
+        v = e ? atoi(e) : 2;
+        if (v < 1 || v > SP_MAX_GROUPS) v = 2;
     }
     return v;
 }
@@ -283,7 +310,7 @@ using namespace pla;
 
 extern "C" size_t pla_stream_pass_workspace_bytes(int64_t m, int64_t n) {
     (void)m;
-    return (size_t)num_sms() * (size_t)(n + 1) * sizeof(double) + 256;
+    return (size_t)num_sms() * SP_MAX_GROUPS * (size_t)(n + 1) * sizeof(double) + 256;
 }
 
 extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
@@ -305,43 +332,32 @@ extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_
     p.A = A; p.m = m; p.n = n; p.lda = lda; p.w = w; p.u = u; p.g = g; p.sc = sc_dev; p.sa = sa; p.su = su;
     p.istop = istop_dev; p.flags = flags;
     const int vec = (n % 2 == 0) ? 2 : 1;
-    const long long groups = (n + (long long)vec * SP_CONS - 1) / ((long long)vec * SP_CONS);
+    const long long groups = (n + (long long)vec * SP_GROUP - 1) / ((long long)vec * SP_GROUP);
     PLA_CHECK_ARG(groups <= 16, 3, "n too large for this vector width (odd n must be <= 4096)");
-    p.R = pick_tile_rows(n, sp_tile_bytes_target());
-    const size_t stage_bytes = (size_t)p.R * n * 8;
-    const size_t budget = 200 * 1024;
-    int stages = (int)(budget / stage_bytes);
-    if (stages > SP_MAX_STAGES) stages = SP_MAX_STAGES;
-    PLA_CHECK_ARG(stages >= 2, 3, "row tile does not fit twice in shared memory");
-    p.stages = stages;
-    p.ntiles = (m + p.R - 1) / p.R;
-    p.use_tma = (lda == n) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (((size_t)p.R * n) % 2 == 0);
-    int grid = num_sms();
-    if ((long long)grid > p.ntiles) grid = (int)p.ntiles;
     p.zpart = reinterpret_cast<double*>(ws);
-    p.sspart = p.zpart + (size_t)num_sms() * n;
-    const size_t smem = (((size_t)stages * stage_bytes + 15) & ~(size_t)15) + 2 * SP_MAX_STAGES * 8 +
-                        2 * (SP_CONS / 32) * SP_RMAX * 8;
+    p.sspart = p.zpart + (size_t)num_sms() * SP_MAX_GROUPS * n;
+    const bool two = sp_groups() == 2;
 
     cudaError_t e;
-#define PLA_SP_CASE(V, JJ) e = launch_pass<V, JJ>(p, grid, smem, st)
+    int nparts = 0;
+#define PLA_SP_CASE(V, JJ, NGG) e = launch_pass<V, JJ, NGG>(p, st, &nparts)
     if (vec == 2) {
-        if (groups <= 1) PLA_SP_CASE(2, 1);
-        else if (groups <= 2) PLA_SP_CASE(2, 2);
-        else if (groups <= 4) PLA_SP_CASE(2, 4);
-        else if (groups <= 8) PLA_SP_CASE(2, 8);
-        else PLA_SP_CASE(2, 16);
+        if (groups <= 1) { if (two) PLA_SP_CASE(2, 1, 2); else PLA_SP_CASE(2, 1, 1); }
+        else if (groups <= 2) { if (two) PLA_SP_CASE(2, 2, 2); else PLA_SP_CASE(2, 2, 1); }
+        else if (groups <= 4) { if (two) PLA_SP_CASE(2, 4, 2); else PLA_SP_CASE(2, 4, 1); }
+        else if (groups <= 8) PLA_SP_CASE(2, 8, 1);
+        else PLA_SP_CASE(2, 16, 1);
     } else {
-        if (groups <= 1) PLA_SP_CASE(1, 1);
-        else if (groups <= 2) PLA_SP_CASE(1, 2);
-        else if (groups <= 4) PLA_SP_CASE(1, 4);
-        else if (groups <= 8) PLA_SP_CASE(1, 8);
-        else PLA_SP_CASE(1, 16);
+        if (groups <= 1) { if (two) PLA_SP_CASE(1, 1, 2); else PLA_SP_CASE(1, 1, 1); }
+        else if (groups <= 2) { if (two) PLA_SP_CASE(1, 2, 2); else PLA_SP_CASE(1, 2, 1); }
+        else if (groups <= 4) { if (two) PLA_SP_CASE(1, 4, 2); else PLA_SP_CASE(1, 4, 1); }
+        else if (groups <= 8) PLA_SP_CASE(1, 8, 1);
+        else PLA_SP_CASE(1, 16, 1);
     }
 #undef PLA_SP_CASE
     if (e != cudaSuccess) { set_error("pla_stream_pass_f64: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     const int rb = (int)((n + 1 + 255) / 256);
-    stream_pass_reduce_kernel<<<rb, 256, 0, st>>>(p.zpart, p.sspart, grid, n, zss, do_axpy ? 1 : 0, istop_dev);
+    stream_pass_reduce_kernel<<<rb, 256, 0, st>>>(p.zpart, p.sspart, nparts, n, zss, do_axpy ? 1 : 0, istop_dev);
     PLA_LAUNCH_CHECK();
     return 0;
 }

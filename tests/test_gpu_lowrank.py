@@ -104,7 +104,8 @@ def test_qb2_tolerance_and_overwrite(rla):
 def test_rs1_power_iteration_improves_alignment(rla):
     """test_aware.py:45-106 in spirit: more passes => S aligns with the dominant right singular space."""
     rng = np.random.default_rng(0)
-    A, U, s, Vt = orc.rand_low_rank(400, 60, np.logspace(0, -3, 60), rng, factors=True)
+    spec = np.concatenate([np.linspace(1.0, 0.8, 5), np.logspace(-1, -3, 55)])          # gap after the 5th value
+    A, U, s, Vt = orc.rand_low_rank(400, 60, spec, rng, factors=True)
     k = 5
     errs = []
     for num_pass in (0, 1, 2, 3, 4, 6):
