@@ -26,6 +26,8 @@ extern "C" {
 int pla_version(void);
 const char* pla_last_error(void);
 int pla_num_sms(void);
+/* Number of kernels this library has launched in this process so far (bench.py's gpu_launches). */
+long long pla_launch_count(void);
 /* Measurement hook: `iters` x 8 independent DMMA.8x8x4 per warp, 8 warps per CTA, ctas_per_sm CTAs per SM.
  * Used once to find the FP64 tensor-pipe peak the Gaussian sketch is graded against.               */
 int pla_dmma_probe(int iters, int ctas_per_sm, double* sink, void* stream);

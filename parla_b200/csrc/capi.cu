@@ -1,5 +1,6 @@
 // Library-level plumbing: version, thread-local error string, device queries.
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 #include "../../include/parla_b200.h"
 
@@ -13,6 +14,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -79,6 +83,7 @@ extern "C" int pla_dmma_probe(int iters, int ctas_per_sm, double* sink, void* st
 extern "C" int pla_version(void) { return 100; }
 extern "C" const char* pla_last_error(void) { return g_err; }
 extern "C" int pla_num_sms(void) { return num_sms(); }
+extern "C" long long pla_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" size_t pla_sumsq_workspace_bytes(int64_t n) {
     (void)n;

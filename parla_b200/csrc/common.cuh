@@ -10,6 +10,7 @@ namespace pla {
 // ------------------------------------------------------------------ host-side error plumbing
 void set_error(const char* fmt, ...);          // capi.cu (thread-local message)
 int num_sms();                                  // capi.cu (cached per current device)
+void note_launch(int n = 1);                    // capi.cu (process-wide kernel-launch counter)
 
 #define PLA_CHECK_ARG(cond, idx, msg)                                             \
     do { if (!(cond)) { ::pla::set_error("%s: bad argument %d: %s", __func__, (idx), (msg)); \
@@ -25,7 +26,8 @@ int num_sms();                                  // capi.cu (cached per current d
     do { cudaError_t e__ = cudaGetLastError();                                    \
          if (e__ != cudaSuccess) {                                                \
              ::pla::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
-             return (int)e__; } } while (0)
+             return (int)e__; }                                                   \
+         ::pla::note_launch(); } while (0)
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -246,10 +246,10 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, bool vec16, cud
     cudaError_t e;
     if (vec16) {
         e = cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) { gemm_f64_kernel<TA, TB, true><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); }
+        if (e == cudaSuccess) { gemm_f64_kernel<TA, TB, true><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); note_launch(); }
     } else {
         e = cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) { gemm_f64_kernel<TA, TB, false><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); }
+        if (e == cudaSuccess) { gemm_f64_kernel<TA, TB, false><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); note_launch(); }
     }
     if (e != cudaSuccess) { set_error("gemm: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     if (zs > 1) {
@@ -258,6 +258,7 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, bool vec16, cud
         if (nb > 4 * num_sms()) nb = 4 * num_sms();
         gemm_splitk_reduce<<<nb, 256, 0, st>>>(p.part, zs, p.M, p.N, p.alpha, p.beta, p.C, p.ldc);
         e = cudaGetLastError();
+        note_launch();
         if (e != cudaSuccess) { set_error("gemm: reduce launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     }
     return 0;

@@ -383,6 +383,7 @@ static int run_panel(double* A, long long lda, long long M, long long j0, int jb
     PLA_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st));
     void* args[] = {(void*)&pp};
     PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
+    note_launch();
     // compact-WY factor T
     int GG = (int)((rows + 4 * QR_TR - 1) / (4 * QR_TR));
     if (GG > sms) GG = sms;

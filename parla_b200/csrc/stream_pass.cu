@@ -291,6 +291,7 @@ static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts
                                          (int)smem);
     if (e != cudaSuccess) return e;
     stream_pass_kernel<VEC, J, NG><<<grid, NG * SP_GROUP + 32, smem, st>>>(p);
+    note_launch();
     return cudaGetLastError();
 }
 

@@ -59,13 +59,28 @@ def dim_checks(sampling_factor, n_rows, n_cols):
 
 
 def _to_device(A, b):
-    """Accept numpy inputs (host buffers): upload, and remember to hand numpy back."""
-    host = isinstance(A, np.ndarray)
-    if host:
+    """Accept HOST buffers (numpy arrays or CPU torch tensors, ideally pinned): upload them on the
+    current stream and remember to hand the result back on the host.  -> (A, b, host_kind)"""
+    host = None
+    if isinstance(A, np.ndarray):
+        host = "numpy"
+        A = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float64))
+        b = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64))
+    elif isinstance(A, torch.Tensor) and not A.is_cuda:
+        host = "torch"
+    if host is not None:
         dev = torch.device("cuda", torch.cuda.current_device())
-        A = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float64)).to(dev, non_blocking=True)
-        b = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(dev, non_blocking=True)
+        A = A.to(dev, non_blocking=True)
+        b = b.to(dev, non_blocking=True)
     return A, b, host
+
+
+def _to_host(x, host):
+    if host == "numpy":
+        return x.cpu().numpy()
+    if host == "torch":
+        return x.cpu()
+    return x
 
 
 def _sketch(sketch_op_gen, d, A, b, delta, rng):
@@ -120,7 +135,7 @@ class SSO1(OverLstsqSolver):
         K.geqrf(W, n_cols)
         x_ske = K.trsv_upper(W[:n_cols, :n_cols], W[:n_cols, n_cols].contiguous())
         log['time_solve'] = quick_time() - tic
-        return (x_ske.cpu().numpy() if host else x_ske), log
+        return _to_host(x_ske, host), log
 
     exec = __call__
 
@@ -224,6 +239,6 @@ class SPO(OverLstsqSolver):
             log.passes_over_A = op.passes + 1      # + the sketch
         self.last_residual = res[1]
         x = res[0]
-        return (x.cpu().numpy() if host else x), log
+        return _to_host(x, host), log
 
     exec = __call__

@@ -17,6 +17,13 @@ LSQR_SA = 15            # dstate[15:17] = (sa, su) of the next pass
 F64 = torch.float64
 
 
+PASS_TIMINGS = None     # set to a list to record (flags, m, n, start_event, end_event) per streaming pass
+
+
+def launch_count():
+    return int(_lib.load().pla_launch_count())
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -86,9 +93,16 @@ def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None,
         zss = torch.empty(n + 1, dtype=F64, device=A.device)
     nb = lib.pla_stream_pass_workspace_bytes(m, n)
     ws = Workspace.get(A.device, nb, "pass")
+    rec = PASS_TIMINGS
+    if rec is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = lib.pla_stream_pass_f64(A.data_ptr(), m, n, lda, _p(w), _p(u), _p(g), _p(sc), float(sa), float(su),
                                  zss.data_ptr(), int(flags), _p(istop), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "pla_stream_pass_f64")
+    if rec is not None:
+        e1.record()
+        rec.append((int(flags), m, n, e0, e1))
     return zss
 
 
