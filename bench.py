@@ -254,7 +254,7 @@ def run_gpu_arm(a):
         have = psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
         note = "full shard in pinned host memory"
         rows_host = m
-        if have < 1.25 * need:
+        if have < 1.6 * need:
             rows_host = max(1 << 14, int(0.6 * have / (n * 8)) // 4096 * 4096)
             note = (f"host RAM per rank allows {rows_host} pinned rows; the e2e solve is run on that many rows and the "
                     f"O(m) part of its time scaled to {m}")

@@ -60,6 +60,13 @@ int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_t lda, cons
 int pla_trsv_upper_f64(const double* R, int64_t n, int64_t ldr, int trans, const double* b, double* x,
                        const int* istop_dev, void* stream);
 
+/* Base case of the blocked inversion of an upper-triangular R: X[32-block diag] = inverse of the
+ * matching diagonal block of R (other entries of X untouched).  The host side completes
+ * X = R^{-1} level by level with pla_gemm_f64 (X12 = -X11 (R12 X22)); the explicit inverse is then
+ * applied with pla_stream_pass_f64, which turns the two sequential solves per LSQR iteration
+ * (preconditioning.py:28,37) into two bandwidth-bound matvecs over an L2-resident matrix.        */
+int pla_trtri_diag_f64(const double* R, int64_t n, int64_t ldr, double* X, int64_t ldx, void* stream);
+
 /* ---------------------------------------------------------------- LSQR recurrences on device
  * Replaces the scalar/vector part of parla/comps/determiter/lsqr.py:342-395 (init) and :412-526
  * (one iteration) so that the host never synchronises inside the loop.

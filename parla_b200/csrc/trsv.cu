@@ -99,9 +99,52 @@ __global__ void __launch_bounds__(TS_THREADS) trsv_upper_t_kernel(const double* 
     for (long long c = threadIdx.x; c < n; c += blockDim.x) xout[c] = x[c];
 }
 
+// Inverse of each 32x32 diagonal block of an upper-triangular matrix (base case of the blocked
+// triangular inversion; the off-diagonal blocks are filled by DMMA GEMMs from the host side:
+// X12 = -X11 (R12 X22)).  One CTA per block, thread j <-> column j (back substitution in smem).
+constexpr int TI_BS = 32;
+__global__ void __launch_bounds__(TI_BS) trtri_diag_kernel(const double* __restrict__ R, long long n, long long ldr,
+                                                           double* X, long long ldx) {
+    __shared__ double Rb[TI_BS][TI_BS + 1];
+    __shared__ double Xb[TI_BS][TI_BS + 1];
+    const long long i0 = (long long)blockIdx.x * TI_BS;
+    const int j = threadIdx.x;
+    const int bs = (int)min((long long)TI_BS, n - i0);
+    for (int r = 0; r < TI_BS; ++r) {
+        double v = (r == j) ? 1.0 : 0.0;                       // identity padding past the matrix edge
+        if (r < bs && j < bs) v = (j >= r) ? R[(i0 + r) * ldr + i0 + j] : 0.0;
+        Rb[r][j] = v;
+    }
+    __syncthreads();
+    for (int i = TI_BS - 1; i >= 0; --i) {
+        double acc = (i == j) ? 1.0 : 0.0;
+        if (i <= j) {
+            for (int l = i + 1; l <= j; ++l) acc = fma(-Rb[i][l], Xb[l][j], acc);
+            acc /= Rb[i][i];
+        } else {
+            acc = 0.0;
+        }
+        Xb[i][j] = acc;                                        // column j only reads its own column of Xb
+    }
+    __syncthreads();
+    for (int r = 0; r < bs; ++r)
+        if (j < bs) X[(i0 + r) * ldx + i0 + j] = Xb[r][j];
+}
+
 }  // namespace pla
 
 using namespace pla;
+
+extern "C" int pla_trtri_diag_f64(const double* R, int64_t n, int64_t ldr, double* X, int64_t ldx, void* stream) {
+    PLA_CHECK_ARG(R != nullptr, 1, "R is null");
+    PLA_CHECK_ARG(n >= 1, 2, "n < 1");
+    PLA_CHECK_ARG(ldr >= n, 3, "ldr < n");
+    PLA_CHECK_ARG(X != nullptr && ldx >= n, 4, "bad X / ldx");
+    trtri_diag_kernel<<<(unsigned)((n + TI_BS - 1) / TI_BS), TI_BS, 0, (cudaStream_t)stream>>>(R, n, ldr, X, ldx);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
 
 extern "C" int pla_trsv_upper_f64(const double* R, int64_t n, int64_t ldr, int trans, const double* b, double* x,
                                   const int* istop_dev, void* stream) {

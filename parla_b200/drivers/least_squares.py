@@ -15,6 +15,7 @@ What differs from the reference's execution, not from its mathematics:
   * ``y = b - A x`` (saddle.py:199) and ``A^T b`` for the log (:361) share one pass over A.
 """
 import math
+import os
 import time
 import warnings
 
@@ -29,6 +30,7 @@ from ..parallel import RowSharded, allreduce_, unwrap
 from ..utils.sketching import as_device_operator, shard_context
 
 F64 = torch.float64
+EXPLICIT_INVERSE = os.environ.get("PLA_EXPLICIT_RINV", "1") != "0"
 
 
 class OverLstsqSolver:
@@ -208,9 +210,19 @@ class SPO(OverLstsqSolver):
         else:
             raise ValueError()
 
+        # The two triangular solves per LSQR iteration (preconditioning.py:28,37) are sequential and
+        # latency-bound; with the explicit inverse they become two bandwidth-bound matvecs over an
+        # L2-resident matrix.  Any fixed nonsingular M gives the same minimiser x = M z, so this only
+        # perturbs the preconditioner by O(cond(R) eps).  (z_ske above is still solved against R.)
+        M_pc, tri_pc = R, tri
+        if tri and n <= K.PASS_MAX_N and EXPLICIT_INVERSE:
+            M_pc, tri_pc = K.trtri_upper(R), False
+            log.time_factor += quick_time() - tic
+            tic = quick_time()
+
         # Presolve acceptance test (:344-352).  b - A x_ske is LSQR's starting residual, so the pass
         # doubles as the solver's initialisation.
-        op = rpc.PrecondOperator(A, delta, R, tri)
+        op = rpc.PrecondOperator(A, delta, M_pc, tri_pc)
         bnorm = math.sqrt(float(allreduce_(K.sumsq(b_loc), group)))
         warm = dict(u=b_loc.clone(),
                     ub=torch.zeros(n, dtype=F64, device=dev) if delta > 0 else None,
@@ -227,7 +239,7 @@ class SPO(OverLstsqSolver):
 
         # Iterative phase                                                           :355-358
         tic = quick_time()
-        res = self.iterative_solver(A, b, None, delta, tol, iter_lim, R, tri, z_ske, _op=op, _warm=warm)
+        res = self.iterative_solver(A, b, None, delta, tol, iter_lim, M_pc, tri_pc, z_ske, _op=op, _warm=warm)
         log.time_iterate = quick_time() - tic
 
         if logging:                                                               # :360-367

@@ -139,6 +139,29 @@ def trsv_upper(R, b, trans=False, out=None, istop=None):
     return out
 
 
+def trtri_upper(R):
+    """Explicit inverse of an upper-triangular matrix (strict lower part of R ignored), blocked:
+    32x32 diagonal blocks by back substitution, then X12 = -X11 (R12 X22) level by level with the
+    DMMA GEMM.  Returns a dense row-major n x n tensor (zeros below the diagonal)."""
+    lib = _lib.load()
+    _req(R, "R")
+    n = R.shape[0]
+    if R.stride(1) != 1:
+        R = R.contiguous()
+    X = torch.zeros(n, n, dtype=F64, device=R.device)
+    _lib.check(lib.pla_trtri_diag_f64(R.data_ptr(), n, R.stride(0), X.data_ptr(), n, _stream()), "pla_trtri_diag_f64")
+    s = 32
+    while s < n:
+        for i0 in range(0, n, 2 * s):
+            i1, i2 = i0 + s, min(i0 + 2 * s, n)
+            if i1 >= n:
+                break
+            T = gemm(R[i0:i1, i1:i2], X[i1:i2, i1:i2])                      # R12 X22
+            gemm(X[i0:i1, i0:i1], T, alpha=-1.0, beta=0.0, out=X[i0:i1, i1:i2])   # X12 = -X11 T
+        s *= 2
+    return X
+
+
 # ---------------------------------------------------------------------------------------- LSQR state
 def lsqr_init(t, zss, bsq, atol, btol, conlim, iter_lim, x0, x, v, w, dstate, istate):
     rc = _lib.load().pla_lsqr_init_f64(x.numel(), t.data_ptr(), zss.data_ptr(), bsq.data_ptr(), float(atol),

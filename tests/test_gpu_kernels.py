@@ -104,6 +104,16 @@ def test_trsv(K, n, trans):
     assert rel(bd, x_ref) < 1e-11
 
 
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 100, 257, 1024, 2048])
+def test_trtri_upper(K, n):
+    rng = np.random.default_rng(n + 5)
+    R = np.linalg.qr(rng.standard_normal((2 * n + 3, n)))[1]
+    W = np.zeros((n, n + 1)); W[:, :n] = R + np.tril(rng.standard_normal((n, n)), -1)   # strided, junk below diag
+    X = K.trtri_upper(dev(W)[:, :n]).cpu().numpy()
+    assert np.allclose(X, np.triu(X))
+    assert np.linalg.norm(X @ R - np.eye(n)) < 1e-11 * n
+
+
 # ------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("M,N,K_", [(1, 1, 1), (37, 29, 53), (128, 128, 64), (200, 130, 1000), (64, 48, 20000),
