@@ -35,24 +35,32 @@ struct GemmParams {
 };
 
 // ---- tile loaders -----------------------------------------------------------------------------
+// Each thread copies the same (row, chunk) slots of every k-tile, so addresses are one base pointer
+// plus compile-time multiples of the leading dimension and the bounds tests are hoisted.
 // Source stored [X][K] (k contiguous): smem tile[x][GM_LDK].   rows x0.., cols k0..
 template <bool VEC16>
 __device__ __forceinline__ void load_xk(double* tile, const double* __restrict__ src, long long ld, long long X,
                                         long long K, long long x0, long long k0) {
-    if (VEC16) {
-        // 128 rows x 8 chunks(16B)
-        for (int idx = threadIdx.x; idx < GM_BM * (GM_BK / 2); idx += GM_THREADS) {
-            const int r = idx >> 3, ch = idx & 7;
-            const long long gx = x0 + r, gk = k0 + 2 * ch;
-            const bool ok = gx < X && gk < K;
-            cp_async16(tile + r * GM_LDK + 2 * ch, ok ? src + gx * ld + gk : src, ok);
+    const int tid = threadIdx.x;
+    if (VEC16) {                       // 128 rows x 8 chunks(16B): thread -> chunk tid&7 of rows (tid>>3) + 32 i
+        const int r0 = tid >> 3, c2 = 2 * (tid & 7);
+        const bool kok = k0 + c2 < K;
+        const double* p = src + (x0 + r0) * ld + k0 + c2;
+        double* d = tile + r0 * GM_LDK + c2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool ok = kok && (x0 + r0 + 32 * i < X);
+            cp_async16(d + 32 * i * GM_LDK, ok ? p + 32 * i * ld : src, ok);
         }
-    } else {
-        for (int idx = threadIdx.x; idx < GM_BM * GM_BK; idx += GM_THREADS) {
-            const int r = idx >> 4, c = idx & 15;
-            const long long gx = x0 + r, gk = k0 + c;
-            const bool ok = gx < X && gk < K;
-            cp_async8(tile + r * GM_LDK + c, ok ? src + gx * ld + gk : src, ok);
+    } else {                           // 128 rows x 16 doubles: thread -> column tid&15 of rows (tid>>4) + 16 i
+        const int r0 = tid >> 4, c = tid & 15;
+        const bool kok = k0 + c < K;
+        const double* p = src + (x0 + r0) * ld + k0 + c;
+        double* d = tile + r0 * GM_LDK + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = kok && (x0 + r0 + 16 * i < X);
+            cp_async8(d + 16 * i * GM_LDK, ok ? p + 16 * i * ld : src, ok);
         }
     }
 }
@@ -62,50 +70,67 @@ template <bool VEC16>
 __device__ __forceinline__ void load_kx(double* tile, const double* __restrict__ src, long long ld, long long X,
                                         long long K, long long x0, long long k0,
                                         const double* __restrict__ xcol = nullptr) {
-    if (VEC16) {
-        // 16 rows x 64 chunks(16B)
-        for (int idx = threadIdx.x; idx < GM_BK * (GM_BM / 2); idx += GM_THREADS) {
-            const int r = idx >> 6, ch = idx & 63;
-            const long long gk = k0 + r, gx = x0 + 2 * ch;
-            double* dst = tile + r * GM_LDX + 2 * ch;
-            if (gx < X || xcol == nullptr || gx != X) {
-                const bool ok = gk < K && gx < X;
-                cp_async16(dst, ok ? src + gk * ld + gx : src, ok);
+    const int tid = threadIdx.x;
+    if (VEC16) {                       // 16 rows x 64 chunks(16B): thread -> chunk tid&63 of rows (tid>>6) + 4 i
+        const int r0 = tid >> 6, c2 = 2 * (tid & 63);
+        const long long gx = x0 + c2;
+        const bool xok = gx < X;
+        const bool extra = (xcol != nullptr) && (gx == X);
+        const double* p = src + (k0 + r0) * ld + gx;
+        double* d = tile + r0 * GM_LDX + c2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool kok = k0 + r0 + 4 * i < K;
+            if (!extra) {
+                const bool ok = xok && kok;
+                cp_async16(d + 4 * i * GM_LDX, ok ? p + 4 * i * ld : src, ok);
             } else {
-                const bool ok = gk < K;
-                cp_async8(dst, ok ? xcol + gk : src, ok);
-                cp_async8(dst + 1, src, false);
+                cp_async8(d + 4 * i * GM_LDX, kok ? xcol + k0 + r0 + 4 * i : src, kok);
+                cp_async8(d + 4 * i * GM_LDX + 1, src, false);
             }
         }
-    } else {
-        for (int idx = threadIdx.x; idx < GM_BK * GM_BM; idx += GM_THREADS) {
-            const int r = idx >> 7, c = idx & 127;
-            const long long gk = k0 + r, gx = x0 + c;
-            double* dst = tile + r * GM_LDX + c;
-            if (xcol != nullptr && gx == X) {
-                const bool ok = gk < K;
-                cp_async8(dst, ok ? xcol + gk : src, ok);
+    } else {                           // 16 rows x 128 doubles: thread -> column tid&127 of rows (tid>>7) + 2 i
+        const int r0 = tid >> 7, c = tid & 127;
+        const long long gx = x0 + c;
+        const bool xok = gx < X;
+        const bool extra = (xcol != nullptr) && (gx == X);
+        const double* p = src + (k0 + r0) * ld + gx;
+        double* d = tile + r0 * GM_LDX + c;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool kok = k0 + r0 + 2 * i < K;
+            if (!extra) {
+                const bool ok = xok && kok;
+                cp_async8(d + 2 * i * GM_LDX, ok ? p + 2 * i * ld : src, ok);
             } else {
-                const bool ok = gk < K && gx < X;
-                cp_async8(dst, ok ? src + gk * ld + gx : src, ok);
+                cp_async8(d + 2 * i * GM_LDX, kok ? xcol + k0 + r0 + 2 * i : src, kok);
             }
         }
     }
 }
 // Generated operator tile: rows = operator rows x0.., k = global column (col_offset + k0 ..). [x][GM_LDK]
+// half = 0/1 generates rows [0,64) / [64,128) of the tile (one Philox block per thread), so the
+// generator's dependent integer chain can be split around DMMA groups; half < 0 does both.
 __device__ __forceinline__ void gen_xk(double* tile, uint64_t seed, long long col_offset, long long X, long long K,
-                                       long long x0, long long k0) {
-    // 128 rows x 4 quads; k0 and col_offset are multiples of 4 by construction
-    for (int idx = threadIdx.x; idx < GM_BM * (GM_BK / 4); idx += GM_THREADS) {
-        const int r = idx >> 2, qd = idx & 3;
-        const long long gx = x0 + r, gk = k0 + 4 * qd;
+                                       long long x0, long long k0, int half) {
+    // 128 rows x 4 quads; thread -> quad tid&3 of rows (tid>>2) + 64 i.  k0, col_offset multiples of 4.
+    const int tid = threadIdx.x;
+    const int r0 = tid >> 2, qd = tid & 3;
+    const long long gk = k0 + 4 * qd;
+    const uint64_t q = (uint64_t)(col_offset + gk) >> 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (half >= 0 && half != i) continue;
+        const long long gx = x0 + r0 + 64 * i;
         double g[4] = {0.0, 0.0, 0.0, 0.0};
         if (gx < X && gk < K) {
-            philox_normal4(seed, (uint32_t)gx, (uint64_t)(col_offset + gk) >> 2, g);
+            philox_normal4(seed, (uint32_t)gx, q, g);
+            if (gk + 4 > K) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (gk + j >= K) g[j] = 0.0;
+                for (int j = 0; j < 4; ++j) if (gk + j >= K) g[j] = 0.0;
+            }
         }
-        double* dst = tile + r * GM_LDK + 4 * qd;
+        double* dst = tile + (r0 + 64 * i) * GM_LDK + 4 * qd;
         *reinterpret_cast<double2*>(dst) = make_double2(g[0], g[1]);
         *reinterpret_cast<double2*>(dst + 2) = make_double2(g[2], g[3]);
     }
@@ -133,31 +158,35 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto issue = [&](int kt_local) {
-        const int slot = kt_local % GM_STAGES;
+    // The two operand tiles of a k-step are fetched by separate helpers so that their address /
+    // predicate / Philox instructions can be interleaved with DMMA groups (tensor pipe stays busy).
+    auto issue_a = [&](int kt_local, int half) {        // half: -1 whole tile, 0/1 first/second part
         const long long k0 = (kt_begin + kt_local) * GM_BK;
-        double* a = sA + slot * GM_TILE;
-        double* b = sB + slot * GM_TILE;
+        double* a = sA + (kt_local % GM_STAGES) * GM_TILE;
+        if (TA == 2) { gen_xk(a, p.seed, p.col_offset, p.M, p.K, m0, k0, half); return; }
+        if (half > 0) return;                            // copied tiles are issued in one piece
         if (TA == 0) load_xk<VEC16>(a, p.A, p.lda, p.M, p.K, m0, k0);
-        else if (TA == 1) load_kx<VEC16>(a, p.A, p.lda, p.M, p.K, m0, k0);
-        else gen_xk(a, p.seed, p.col_offset, p.M, p.K, m0, k0);
+        else load_kx<VEC16>(a, p.A, p.lda, p.M, p.K, m0, k0);
+    };
+    auto issue_b = [&](int kt_local) {
+        const long long k0 = (kt_begin + kt_local) * GM_BK;
+        double* b = sB + (kt_local % GM_STAGES) * GM_TILE;
         if (TB == 0) load_kx<VEC16>(b, p.B, p.ldb, p.Nb, p.K, n0, k0, p.xcol);
         else load_xk<VEC16>(b, p.B, p.ldb, p.Nb, p.K, n0, k0);
     };
 
 #pragma unroll
     for (int s = 0; s < GM_STAGES - 1; ++s) {
-        if (s < nkt) issue(s);
+        if (s < nkt) { issue_a(s, -1); issue_b(s); }
         cp_async_commit();
     }
     const int fr = lane >> 2, fc = lane & 3;            // fragment row / k (A), k / col (B)
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<GM_STAGES - 2>();
-        __syncthreads();
-        if (kt + GM_STAGES - 1 < nkt) issue(kt + GM_STAGES - 1);
-        cp_async_commit();
+        __syncthreads();                                 // tile kt landed; slot (kt-1)%STAGES is free again
         const double* a = sA + (kt % GM_STAGES) * GM_TILE;
         const double* b = sB + (kt % GM_STAGES) * GM_TILE;
+        const bool more = kt + GM_STAGES - 1 < nkt;
 #pragma unroll
         for (int kk = 0; kk < GM_BK; kk += 4) {
             double af[8], bf[4];
@@ -175,6 +204,11 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            // prefetch of tile kt+STAGES-1 rides in the shadow of the DMMAs just issued
+            if (kk == 0 && more) issue_a(kt + GM_STAGES - 1, 0);
+            if (kk == 4 && more) issue_b(kt + GM_STAGES - 1);
+            if (kk == 4) cp_async_commit();
+            if (kk == 8 && more) issue_a(kt + GM_STAGES - 1, 1);
         }
     }
     cp_async_wait<0>();
@@ -219,14 +253,20 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce(const double* __restri
 static int choose_splits(long long M, long long N, long long K) {
     const long long tiles = ((M + GM_BM - 1) / GM_BM) * ((N + GM_BN - 1) / GM_BN);
     const long long ktiles = (K + GM_BK - 1) / GM_BK;
-    const int sms = num_sms();
-    if (tiles >= sms || ktiles < 32) return 1;
-    long long s = (2LL * sms + tiles - 1) / tiles;      // aim at ~2 CTAs' worth of work per SM
-    const long long max_by_k = ktiles / 16;             // keep >= 16 k-tiles per split
-    if (s > max_by_k) s = max_by_k;
-    if (s > 64) s = 64;
-    if (s < 1) s = 1;
-    return (int)s;
+    const long long sms = num_sms();
+    if (tiles >= 4 * sms || ktiles < 64) return 1;
+    // pick the split count whose CTA count fills whole waves best (>= 32 k-tiles per split)
+    long long smax = ktiles / 32;
+    if (smax > 64) smax = 64;
+    int best = 1;
+    double best_eff = (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);
+    for (long long sp = 2; sp <= smax; ++sp) {
+        const long long ctas = tiles * sp;
+        const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = (int)sp; }
+        if (ctas >= 8 * sms) break;
+    }
+    return best;
 }
 
 template <int TA, int TB>
@@ -264,6 +304,36 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, bool vec16, cud
     return 0;
 }
 
+// out_b[r] (+)= scale * sum_i G[r, off+i] b[i]: one warp per (operator row, k-split); partials reduced in order.
+__global__ void __launch_bounds__(256) gauss_matvec_kernel(const double* __restrict__ b, long long m, long long d,
+                                                           uint64_t seed, long long col_offset, long long k_per_split,
+                                                           double* part) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= d) return;
+    const long long kb = (long long)blockIdx.y * k_per_split;
+    long long ke = kb + k_per_split;
+    if (ke > m) ke = m;
+    double acc = 0.0;
+    for (long long k = kb + 4 * lane; k < ke; k += 128) {
+        double g[4];
+        philox_normal4(seed, (uint32_t)r, (uint64_t)(col_offset + k) >> 2, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k + j < ke) acc = fma(g[j], b[k + j], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) part[(size_t)blockIdx.y * d + r] = acc;
+}
+__global__ void __launch_bounds__(256) gauss_matvec_reduce(const double* __restrict__ part, int splits, long long d,
+                                                           double scale, double beta, double* out, long long ldo) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d) return;
+    double acc = 0.0;
+    for (int s = 0; s < splits; ++s) acc += part[(size_t)s * d + r];
+    out[r * ldo] = (beta == 0.0) ? scale * acc : fma(scale, acc, beta * out[r * ldo]);
+}
+
 static bool aligned16(const void* ptr, long long ld) { return ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld % 2 == 0); }
 
 }  // namespace pla
@@ -299,7 +369,9 @@ extern "C" int pla_gemm_f64(int transa, int transb, int64_t M, int64_t N, int64_
 }
 
 extern "C" size_t pla_sketch_gauss_workspace_bytes(int64_t d, int64_t n, int64_t m) {
-    return pla_gemm_workspace_bytes(d, n + 1, m);     // sized for the optional rhs column
+    size_t a = pla_gemm_workspace_bytes(d, n + 1, m), b = pla_gemm_workspace_bytes(d, n, m);
+    size_t c = (size_t)d * 8 * 64;                    // k-split partials of the separate rhs sketch
+    return (a > b ? a : b) > c ? (a > b ? a : b) : c;
 }
 
 extern "C" int pla_sketch_gauss_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* bvec, int64_t d,
@@ -312,12 +384,34 @@ extern "C" int pla_sketch_gauss_f64(const double* A, int64_t m, int64_t n, int64
     PLA_CHECK_ARG(col_offset >= 0 && col_offset % 4 == 0, 8, "col_offset must be a non-negative multiple of 4");
     const int64_t ncols = n + (bvec != nullptr ? 1 : 0);
     PLA_CHECK_ARG(out != nullptr && ldo >= ncols, 11, "bad out / ldo");
+    cudaStream_t st = (cudaStream_t)stream;
+    // The rhs rides as an extra logical column of A unless that would open a whole new 128-column
+    // tile (n a multiple of 128): then S @ b is a separate generate-and-dot kernel (~1 % of the work).
+    const bool separate_b = (bvec != nullptr) && (n % GM_BN == 0) && (m % 4 == 0);
     GemmParams p;
-    p.A = nullptr; p.lda = 0; p.B = A; p.ldb = lda; p.C = out; p.ldc = ldo; p.M = d; p.N = ncols; p.K = m;
-    p.Nb = n; p.xcol = bvec;
+    p.A = nullptr; p.lda = 0; p.B = A; p.ldb = lda; p.C = out; p.ldc = ldo; p.M = d; p.K = m;
+    p.N = separate_b ? n : ncols;
+    p.Nb = n; p.xcol = separate_b ? nullptr : bvec;
     p.alpha = scale; p.beta = beta; p.seed = seed; p.col_offset = col_offset; p.part = nullptr;
     const bool vec16 = aligned16(A, lda) && (n % 2 == 0);
-    return launch_gemm<2, 0>(p, ws, ws_bytes, vec16, (cudaStream_t)stream);
+    int rc = launch_gemm<2, 0>(p, ws, ws_bytes, vec16, st);
+    if (rc != 0 || !separate_b) return rc;
+    // workspace is free again once the GEMM (and its split-K reduce) are enqueued on the same stream
+    int splits = (int)((4LL * num_sms() * 8 + d - 1) / d);
+    if (splits < 1) splits = 1;
+    const long long max_splits = (long long)(ws_bytes / ((size_t)d * 8));
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits > 4096) splits = 4096;
+    if (splits < 1) { set_error("pla_sketch_gauss_f64: workspace too small for the rhs sketch"); return -13; }
+    long long kps = ((m + splits - 1) / splits + 127) / 128 * 128;
+    splits = (int)((m + kps - 1) / kps);
+    dim3 grid((unsigned)((d + 7) / 8), (unsigned)splits);
+    gauss_matvec_kernel<<<grid, 256, 0, st>>>(bvec, m, d, seed, col_offset, kps, (double*)ws);
+    PLA_LAUNCH_CHECK();
+    gauss_matvec_reduce<<<(unsigned)((d + 255) / 256), 256, 0, st>>>((const double*)ws, splits, d, scale, beta,
+                                                                      out + n, ldo);
+    PLA_LAUNCH_CHECK();
+    return 0;
 }
 
 namespace pla {

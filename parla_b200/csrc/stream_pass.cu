@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(NG * SP_GROUP + 32, 1) stream_pass_kernel(cons
                 double tot = 0.0;
 #pragma unroll
                 for (int k = 0; k < NW; ++k) tot += myred[k * SP_RMAX + r];
-                unew[r] = fma(sa, tot, su * uo[r]);
+                unew[r] = (su != 0.0) ? fma(sa, tot, su * uo[r]) : sa * tot;     // su == 0: u is write-only (may be uninitialised)
             }
             flip ^= 1;
             if (gt < rows) {

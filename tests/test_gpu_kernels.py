@@ -56,6 +56,9 @@ def test_stream_pass_modes_and_device_scalars(K):
                         flags=K.PASS_DOT | K.PASS_AXPY | K.PASS_AXPY_G).cpu().numpy()
     assert rel(r, b - A @ x) < 1e-13
     assert np.linalg.norm(zss[:n] - A.T @ g) < 1e-12 * np.linalg.norm(A.T @ g)
+    y_nan = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")   # su == 0: output only
+    K.stream_pass(Ad, w=dev(x), u=y_nan, sa=2.0, su=0.0, flags=K.PASS_DOT)
+    assert rel(y_nan, 2 * (A @ x)) < 1e-13
     stop = torch.ones(1, dtype=torch.int32, device="cuda")            # istop set => no-op
     r2 = dev(b)
     K.stream_pass(Ad, w=dev(x), u=r2, sa=5.0, su=0.0, flags=K.PASS_DOT, istop=stop)
