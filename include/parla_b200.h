@@ -130,7 +130,10 @@ int pla_sjlt_plan_f64(const int32_t* rows, const int8_t* signs, int64_t m, int64
                       void* ws, size_t ws_bytes, void* stream);
 int pla_sjlt_apply_f64(const void* plan, int64_t d, int64_t m, int64_t k, const double* A, int64_t n,
                        int64_t lda, const double* bvec, double scale, double* out, int64_t ldo, double* out_b,
-                       int64_t ldob, int accumulate, void* stream);
+                       int64_t ldob, int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* Optional scratch (0 bytes when d*n already fills the GPU): lets small outputs split every destination
+ * list over several warps; the segment sums are added in a fixed order (still deterministic).     */
+size_t pla_sjlt_apply_workspace_bytes(int64_t d, int64_t n);
 /* Validation hook (SYNCHRONISES): number of out-of-range row indices seen while planning.          */
 int pla_sjlt_plan_status(const void* plan, int64_t* bad_index_count_host);
 /* Native (throughput) operator: index form generated on device from Philox4x32-10; column i of S

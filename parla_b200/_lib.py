@@ -32,7 +32,8 @@ SIGNATURES = {
     "pla_sjlt_plan_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pla_sjlt_plan_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "pla_sjlt_apply_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_dbl, c_vp, c_i64, c_vp,
-                                   c_i64, c_int, c_vp]),
+                                   c_i64, c_int, c_vp, c_sz, c_vp]),
+    "pla_sjlt_apply_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "pla_sjlt_plan_status": (c_int, [c_vp, C.POINTER(c_i64)]),
     "pla_sjlt_generate": (c_int, [c_i64, c_i64, c_i64, c_u64, c_i64, c_vp, c_vp, c_vp]),
     "pla_gemm_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),

@@ -91,11 +91,14 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(const PanelParams 
             mypart[tid] = acc;
         }
         grid_barrier(p.counter, (unsigned int)(j + 1) * G);
-        if (tid < QR_NP) {
-            const double* gp = p.gpart + (size_t)(j & 1) * G * QR_NP + tid;
-            double acc = 0.0;
-            for (int b = 0; b < G; ++b) acc += __ldcg(gp + (size_t)b * QR_NP);
-            red[tid] = acc;
+        {   // fixed-order sum of the G per-CTA partials: lane <-> CTA, warp <-> column (loads in parallel)
+            const double* gp = p.gpart + (size_t)(j & 1) * G * QR_NP;
+            for (int c = wid; c < QR_NP; c += QR_THREADS / 32) {
+                double acc = 0.0;
+                for (int b = lane; b < G; b += 32) acc += __ldcg(gp + (size_t)b * QR_NP + c);
+                acc = warp_sum(acc);
+                if (lane == 0) red[c] = acc;
+            }
         }
         __syncthreads();
 
@@ -210,18 +213,19 @@ __global__ void __launch_bounds__(QR_THREADS) qr_build_t_kernel(const double* gp
     G[threadIdx.x / QR_NB][threadIdx.x % QR_NB] = acc;
     Ts[threadIdx.x / QR_NB][threadIdx.x % QR_NB] = 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int j = 0; j < jb; ++j) {
-            const double tj = tau[j];
+    // column j of T needs columns < j: sequential over j, rows of a column in parallel (thread r <-> row r)
+    for (int j = 0; j < jb; ++j) {
+        const double tj = tau[j];
+        const int r = threadIdx.x;
+        if (r < j) {
+            double sacc = 0.0;
+            for (int l = r; l < j; ++l) sacc = fma(Ts[r][l], G[l][j], sacc);
+            Ts[r][j] = -tj * sacc;
+        } else if (r == j) {
             Ts[j][j] = tj;
-            for (int r = 0; r < j; ++r) {
-                double s = 0.0;
-                for (int l = r; l < j; ++l) s = fma(Ts[r][l], G[l][j], s);
-                Ts[r][j] = -tj * s;
-            }
         }
+        __syncthreads();
     }
-    __syncthreads();
     T[threadIdx.x] = Ts[threadIdx.x / QR_NB][threadIdx.x % QR_NB];
 }
 

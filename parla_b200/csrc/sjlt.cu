@@ -113,14 +113,31 @@ __global__ void __launch_bounds__(256) sjlt_apply_kernel(const long long* __rest
                                                          const double* __restrict__ A, long long n, long long lda,
                                                          const double* __restrict__ bvec, double scale, double* out,
                                                          long long ldo, double* out_b, long long ldob,
-                                                         int accumulate, long long nchunks) {
+                                                         int accumulate, long long nchunks, int splits,
+                                                         double* part) {
+    // splits > 1: every destination list is cut into `splits` segments handled by different warps
+    // (more parallelism when d * n is small); segment sums go to part[seg][d][n+1] and are added in
+    // segment order by sjlt_reduce_kernel.
     constexpr int CW = 32 * VEC * J;                    // chunk width in columns
     const int lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (task >= nchunks * d) return;
-    const long long chunk = task / d, r = task - chunk * d;
+    if (task >= nchunks * d * splits) return;
+    const int seg = (int)(task % splits);
+    const long long cr = task / splits;
+    const long long chunk = cr / d, r = cr - chunk * d;
     const long long c0 = chunk * CW;
-    const long long beg = offsets[r], end = offsets[r + 1];
+    long long beg = offsets[r], end = offsets[r + 1];
+    if (splits > 1) {
+        const long long len = end - beg;
+        const long long b2 = beg + len * seg / splits, e2 = beg + len * (seg + 1) / splits;
+        beg = b2; end = e2;
+        out = part + (size_t)seg * d * (n + 1);
+        ldo = n + 1;
+        out_b = (bvec != nullptr) ? out + n : nullptr;
+        ldob = n + 1;
+        accumulate = 0;
+        scale = 1.0;
+    }
     double acc[J * VEC];
 #pragma unroll
     for (int j = 0; j < J * VEC; ++j) acc[j] = 0.0;
@@ -169,6 +186,21 @@ __global__ void __launch_bounds__(256) sjlt_apply_kernel(const long long* __rest
     if (do_b && out_b != nullptr) {
         bacc = warp_sum(bacc);
         if (lane == 0) out_b[r * ldob] = accumulate ? out_b[r * ldob] + scale * bacc : scale * bacc;
+    }
+}
+
+__global__ void __launch_bounds__(256) sjlt_reduce_kernel(const double* __restrict__ part, int splits, long long d,
+                                                          long long n, int with_b, double scale, double* out,
+                                                          long long ldo, double* out_b, long long ldob, int accumulate) {
+    const long long total = d * (n + 1);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / (n + 1), c = idx - r * (n + 1);
+        if (c == n && !with_b) continue;
+        double acc = 0.0;
+        for (int sgm = 0; sgm < splits; ++sgm) acc += part[(size_t)sgm * total + idx];
+        double* dst = (c == n) ? out_b + r * ldob : out + r * ldo + c;
+        *dst = accumulate ? *dst + scale * acc : scale * acc;
     }
 }
 
@@ -254,9 +286,27 @@ extern "C" int pla_sjlt_plan_f64(const int32_t* rows, const int8_t* signs, int64
     return 0;
 }
 
+static int sjlt_splits(long long d, long long nchunks, long long n, size_t ws_bytes) {
+    const long long warps = d * nchunks, want = 4LL * num_sms() * 8;
+    long long sp = (want + warps - 1) / warps;
+    if (sp > 16) sp = 16;
+    const long long fit = (long long)(ws_bytes / ((size_t)d * (size_t)(n + 1) * 8));
+    if (sp > fit) sp = fit;
+    return sp < 2 ? 1 : (int)sp;
+}
+
+extern "C" size_t pla_sjlt_apply_workspace_bytes(int64_t d, int64_t n) {
+    const long long nchunks = (n + 255) / 256;
+    const long long warps = d * nchunks, want = 4LL * num_sms() * 8;
+    long long sp = (want + warps - 1) / warps;
+    if (sp > 16) sp = 16;
+    return sp < 2 ? 0 : (size_t)sp * d * (n + 1) * 8;
+}
+
 extern "C" int pla_sjlt_apply_f64(const void* plan, int64_t d, int64_t m, int64_t k, const double* A, int64_t n,
                                   int64_t lda, const double* bvec, double scale, double* out, int64_t ldo,
-                                  double* out_b, int64_t ldob, int accumulate, void* stream) {
+                                  double* out_b, int64_t ldob, int accumulate, void* ws, size_t ws_bytes,
+                                  void* stream) {
     PLA_CHECK_ARG(plan != nullptr, 1, "plan is null");
     PLA_CHECK_ARG(d >= 1 && m >= 1 && k >= 1, 2, "bad dims");
     PLA_CHECK_ARG(A != nullptr && n >= 1 && lda >= n, 5, "bad A / n / lda");
@@ -268,18 +318,25 @@ extern "C" int pla_sjlt_apply_f64(const void* plan, int64_t d, int64_t m, int64_
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec2 = (n % 2 == 0) && (lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
     const int warps_per_cta = 8;
-    if (vec2) {
-        const long long cw = 256, nchunks = (n + cw - 1) / cw;
-        const long long ctas = (nchunks * d + warps_per_cta - 1) / warps_per_cta;
+    const long long cw = vec2 ? 256 : 128, nchunks = (n + cw - 1) / cw;
+    const int splits = (ws != nullptr) ? sjlt_splits(d, nchunks, n, ws_bytes) : 1;
+    const long long ctas = (nchunks * d * splits + warps_per_cta - 1) / warps_per_cta;
+    double* part = splits > 1 ? (double*)ws : nullptr;
+    if (vec2)
         sjlt_apply_kernel<2, 4><<<(unsigned)ctas, 256, 0, st>>>(offsets, entries, d, A, n, lda, bvec, scale, out, ldo,
-                                                               out_b, ldob, accumulate, nchunks);
-    } else {
-        const long long cw = 128, nchunks = (n + cw - 1) / cw;
-        const long long ctas = (nchunks * d + warps_per_cta - 1) / warps_per_cta;
+                                                               out_b, ldob, accumulate, nchunks, splits, part);
+    else
         sjlt_apply_kernel<1, 4><<<(unsigned)ctas, 256, 0, st>>>(offsets, entries, d, A, n, lda, bvec, scale, out, ldo,
-                                                               out_b, ldob, accumulate, nchunks);
-    }
+                                                               out_b, ldob, accumulate, nchunks, splits, part);
     PLA_LAUNCH_CHECK();
+    if (splits > 1) {
+        long long total = d * (n + 1);
+        int nb = (int)((total + 255) / 256);
+        if (nb > 8 * num_sms()) nb = 8 * num_sms();
+        sjlt_reduce_kernel<<<nb, 256, 0, st>>>(part, splits, d, n, bvec != nullptr ? 1 : 0, scale, out, ldo, out_b,
+                                               ldob, accumulate);
+        PLA_LAUNCH_CHECK();
+    }
     return 0;
 }
 

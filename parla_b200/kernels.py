@@ -270,9 +270,11 @@ class SjltPlan:
         if m != self.m:
             raise ValueError(f"SJLT has {self.m} columns but A has {m} rows")
         ldob = out_b.stride(0) if (out_b is not None and out_b.numel() > 1) else 1
+        nb = lib.pla_sjlt_apply_workspace_bytes(self.d, n)
+        ws = Workspace.get(A.device, nb, "sjlt_apply") if nb else None
         rc = lib.pla_sjlt_apply_f64(self.buf.data_ptr(), self.d, self.m, self.k, A.data_ptr(), n, lda, _p(bvec),
                                     float(scale), out.data_ptr(), out.stride(0), _p(out_b), ldob,
-                                    1 if accumulate else 0, _stream())
+                                    1 if accumulate else 0, _p(ws), ws.numel() if ws is not None else 0, _stream())
         _lib.check(rc, "pla_sjlt_apply_f64")
         return out
 

@@ -157,7 +157,7 @@ def test_philox_fill_matches_oracle_definition(K):
 
 
 @pytest.mark.parametrize("m,n,d,with_b", [(1000, 40, 160, True), (5003, 129, 300, True), (4096, 256, 512, False),
-                                          (70000, 64, 128, True)])
+                                          (70000, 64, 128, True), (6000, 128, 300, True), (4100, 256, 512, True)])
 def test_sketch_gauss_equals_materialised_operator(K, m, n, d, with_b):
     rng = np.random.default_rng(m + n)
     A, b = rng.standard_normal((m, n)), rng.standard_normal(m)
