@@ -28,7 +28,7 @@ class PcSS2(PrecondSaddleSolver):
     def __init__(self):
         self.last_op = None
 
-    def __call__(self, A, b, c, delta, tol, iter_lim, R, upper_tri, z0, _op=None, _warm=None):
+    def __call__(self, A, b, c, delta, tol, iter_lim, R, upper_tri, z0, _op=None, _warm=None, _need_y=True):
         k = 1 if (b is None or b.ndim == 1) else b.shape[1]
         A_pc = _op if _op is not None else a_lift_precond(A, delta, R, upper_tri, k)[0]
         self.last_op = A_pc
@@ -36,7 +36,8 @@ class PcSS2(PrecondSaddleSolver):
             b_loc = getattr(b, "local", b)
             result = lsqr(A_pc, b_loc, atol=tol, btol=tol, iter_lim=iter_lim, x0=z0, _warm=_warm)
             x = A_pc.precond(result[0])
-            y = A_pc.residual_and_atb(x, b_loc)          # y = b - A x  (and A^T b for the log)
+            # y = b - A x (saddle.py:199) costs a pass over A; SPO discards it, so it may opt out
+            y = A_pc.residual_and_atb(x, b_loc) if _need_y else None
             return x, y, result[7]
         if b is None or float(torch.linalg.vector_norm(getattr(b, "local", b))) == 0:
             raise NotImplementedError("under-determined branch (saddle.py:203-214) is not on the hot path yet")

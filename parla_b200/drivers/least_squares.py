@@ -239,7 +239,11 @@ class SPO(OverLstsqSolver):
 
         # Iterative phase                                                           :355-358
         tic = quick_time()
-        res = self.iterative_solver(A, b, None, delta, tol, iter_lim, M_pc, tri_pc, z_ske, _op=op, _warm=warm)
+        # y = b - A x is not part of SPO's result (least_squares.py:369 returns res[0] only); the pass
+        # that produces it is kept only when logging needs A^T b from the same read of A.
+        need_pass = bool(logging) and not (z_ske is None)
+        res = self.iterative_solver(A, b, None, delta, tol, iter_lim, M_pc, tri_pc, z_ske, _op=op, _warm=warm,
+                                    _need_y=need_pass)
         log.time_iterate = quick_time() - tic
 
         if logging:                                                               # :360-367
