@@ -9,7 +9,9 @@ import warnings
 import numpy as np
 import torch
 
+from .. import distla
 from .. import kernels as K
+from ..parallel import RowSharded
 from .rangefinders import RangeFinder
 
 F64 = torch.float64
@@ -38,7 +40,7 @@ class QB1(QBDecomposer):
             assert tol < 1
         rng = np.random.default_rng(rng)
         Q = self.rangefinder(A, k, tol, rng)
-        B = K.gemm(Q, A, transa=True)                              # :351
+        B = distla.mm_t(Q, A)                                      # :351
         return Q, B
 
     exec = __call__
@@ -50,8 +52,8 @@ def project_out(Qi, Q, as_list=False):
         raise NotImplementedError()
     if Q.shape[1] == 0:
         return Qi
-    C = K.gemm(Q, Qi, transa=True)
-    return K.gemm(Q, C, alpha=-1.0, beta=1.0, out=Qi.clone())
+    C = distla.mm_t(Q, Qi)
+    return distla.sub_outer_(distla.clone(Qi), Q, C)
 
 
 class QB2(QBDecomposer):
@@ -65,7 +67,7 @@ class QB2(QBDecomposer):
 
     def __call__(self, A, k, tol, rng):
         if not self.overwrite_a:                                   # qb.py:442-443
-            A = A.clone()
+            A = distla.clone(A)
         assert k > 0
         small_dim = min(A.shape)
         if not k <= small_dim:                                     # :445-452
@@ -78,30 +80,37 @@ class QB2(QBDecomposer):
         assert k <= min(A.shape)
         use_tol = not np.isnan(tol) and tol > 0                    # :454
         if use_tol:
-            sq_norm_A = float(K.sumsq(A.reshape(-1)))
+            sq_norm_A = float(distla.sumsq_all(A))
             abs_sq_tol = sq_norm_A * tol ** 2
         rng = np.random.default_rng(rng)
         m, n = A.shape
-        Q = torch.empty(m, k, dtype=F64, device=A.device)
+        sharded = isinstance(A, RowSharded)
+        m_loc = A.local.shape[0] if sharded else m
+        Qbuf = torch.empty(m_loc, k, dtype=F64, device=A.device)
         B = torch.empty(k, n, dtype=F64, device=A.device)
+
+        def q_view(c0, c1):
+            v = Qbuf[:, c0:c1]
+            return RowSharded(v, A.row_offset, A.m_global, A.group) if sharded else v
+
         cols = 0
         blk = self.blk
         while True:                                                # :463-481
             if cols + blk > k:
                 blk = k - cols  # final block
             Qi = self.rangefinder(A, blk, np.nan, rng)
-            Qi = project_out(Qi, Q[:, :cols])
-            Qi = K.qr_economic(Qi)[0]
-            Bi = K.gemm(Qi, A, transa=True, out=B[cols:cols + blk])
-            Q[:, cols:cols + blk] = Qi
+            Qi = project_out(Qi, q_view(0, cols))
+            Qi = distla.orth(Qi)
+            Bi = distla.mm_t(Qi, A, out=B[cols:cols + blk])
+            Qbuf[:, cols:cols + blk] = distla.local(Qi)
             cols += blk
-            K.gemm(Qi, Bi, alpha=-1.0, beta=1.0, out=A)            # A -= Qi @ Bi
+            distla.sub_outer_(A, Qi, Bi)                           # A -= Qi @ Bi
             if use_tol:
                 sq_norm_A = sq_norm_A - float(K.sumsq(Bi.reshape(-1)))
                 if sq_norm_A <= abs_sq_tol:
                     break
             if cols >= k:
                 break
-        return Q[:, :cols], B[:cols]
+        return q_view(0, cols), B[:cols]
 
     exec = __call__

@@ -3,7 +3,7 @@ import warnings
 
 import numpy as np
 
-from .. import kernels as K
+from .. import distla
 from .sketchers.aware import RowSketcher
 
 
@@ -31,7 +31,7 @@ class RF1(RangeFinder):
             warnings.warn(msg)
         rng = np.random.default_rng(rng)
         S = self.rso(A, k, rng)
-        Y = K.gemm(A, S)                                           # :186
-        return K.qr_economic(Y)[0]                                 # :187
+        Y = distla.mm(A, S)                                        # :186
+        return distla.orth(Y)                                      # :187
 
     exec = __call__

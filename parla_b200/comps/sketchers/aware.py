@@ -6,12 +6,26 @@ All products with A are FP64 DMMA GEMMs (pla_gemm_f64); the stabiliser is normal
 """
 import numpy as np
 
-from ... import kernels as K
-from ...utils.sketching import as_device_operator
+from ... import distla
+from ...parallel import RowSharded
+from ...utils.sketching import as_device_operator, shard_context
 
 
 def _dense(S):
     return as_device_operator(S).to_dense()
+
+
+def _tall_test_matrix(gen, A, k, rng):
+    """gen(m, k, rng) restricted to this rank's rows of A (row-sharded A) or in full."""
+    if not isinstance(A, RowSharded):
+        return _dense(gen(A.shape[0], k, rng))
+    S = as_device_operator(gen(A.shape[0], k, rng))
+    if hasattr(S, "seed"):                               # virtual Gaussian: generate only the local rows
+        from ... import kernels as K
+        loc = K.philox_normal_fill(A.local.shape[0], k, S.seed, S.scale, row_offset=A.row_offset, device=A.device)
+    else:
+        loc = S.to_dense()[A.row_offset:A.row_offset + A.local.shape[0]].contiguous()
+    return RowSharded(loc, A.row_offset, A.m_global, A.group)
 
 
 def rs1(A, k, num_pass, rng, stabilizer, passes_per_stab=1, sketch_op_gen=None):
@@ -44,17 +58,17 @@ class RS1(RowSketcher):
         if self.num_pass % 2 == 0:                                  # :163-164
             S = _dense(self.sketch_op_gen(A.shape[1], k, rng))
         else:                                                       # :165-169
-            S = K.gemm(A, _dense(self.sketch_op_gen(A.shape[0], k, rng)), transa=True)
+            S = distla.mm_t(A, _tall_test_matrix(self.sketch_op_gen, A, k, rng))
             passes_done += 1
             if self.passes_per_stab == 1:
                 S = self.stabilizer(S)
         q = (self.num_pass - passes_done) // 2
         while q > 0:                                                # :174-183
-            S = K.gemm(A, S)
+            S = distla.mm(A, S)
             passes_done += 1
             if passes_done % self.passes_per_stab == 0:
                 S = self.stabilizer(S)
-            S = K.gemm(A, S, transa=True)
+            S = distla.mm_t(A, S)
             passes_done += 1
             if passes_done % self.passes_per_stab == 0:
                 S = self.stabilizer(S)

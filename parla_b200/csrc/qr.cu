@@ -235,6 +235,7 @@ struct TrailParams {
     double* C; long long ldc; long long nc;          // C = columns to update (pointer already offset)
     long long rows_per_split; int splits;
     double* wpart;                                    // [splits][16][nc]
+    double* w2;                                       // [16][nc] = op(T) * sum_splits wpart
     const double* T; int t_transpose;                 // apply T^T (QR) or T (forming Q)
 };
 
@@ -276,31 +277,54 @@ __global__ void __launch_bounds__(QR_THREADS) qr_trail_w_kernel(const TrailParam
     }
 }
 
-// ---- step 2: W = op(T) * sum_splits Wpart ;  C -= V W
+// ---- step 2a: W2 = op(T) * (sum over row splits of Wpart), once per column (fixed summation order)
+// block = 32 columns x 8 split-groups; partial sums over split-groups are combined in group order.
+__global__ void __launch_bounds__(QR_THREADS) qr_trail_reduce_kernel(const TrailParams p) {
+    __shared__ double acc_s[8][QR_NB][33];
+    __shared__ double Ts[QR_NB][QR_NB];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * 32 + cl;
+    Ts[threadIdx.x / QR_NB][threadIdx.x % QR_NB] = p.T[threadIdx.x];
+    double acc[QR_NB];
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) acc[k] = 0.0;
+    if (c < p.nc) {
+        for (int sp = grp; sp < p.splits; sp += 8) {
+            const double* src = p.wpart + (size_t)sp * QR_NB * p.nc + c;
+#pragma unroll
+            for (int k = 0; k < QR_NB; ++k) acc[k] += src[(size_t)k * p.nc];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < QR_NB; ++k) acc_s[grp][k][cl] = acc[k];
+    __syncthreads();
+    // thread (k = grp*2 + h, column cl): w[l] = sum_groups acc_s[g][l][cl];  W2[k] = sum_l op(T)[k][l] w[l]
+    if (c < p.nc) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = grp * 2 + h;
+            double sacc = 0.0;
+            for (int l = 0; l < QR_NB; ++l) {
+                double wl = 0.0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) wl += acc_s[g][l][cl];
+                sacc = fma(p.t_transpose ? Ts[l][k] : Ts[k][l], wl, sacc);
+            }
+            p.w2[(size_t)k * p.nc + c] = sacc;
+        }
+    }
+}
+
+// ---- step 2b: C -= V W2
 __global__ void __launch_bounds__(QR_THREADS) qr_trail_apply_kernel(const TrailParams p) {
     __shared__ __align__(16) double vt[QR_TR][QR_NB];
-    __shared__ double Ts[QR_NB][QR_NB];
     const long long c = (long long)blockIdx.x * QR_THREADS + threadIdx.x;
     const long long r_begin = p.V.j0 + (long long)blockIdx.y * p.rows_per_split;
     long long r_end = r_begin + p.rows_per_split;
     if (r_end > p.M) r_end = p.M;
-    Ts[threadIdx.x / QR_NB][threadIdx.x % QR_NB] = p.T[threadIdx.x];
-    __syncthreads();
-    double w[QR_NB], w2[QR_NB];
+    double w2[QR_NB];
 #pragma unroll
-    for (int k = 0; k < QR_NB; ++k) {
-        double s = 0.0;
-        if (c < p.nc)
-            for (int sp = 0; sp < p.splits; ++sp) s += p.wpart[((size_t)sp * QR_NB + k) * p.nc + c];
-        w[k] = s;
-    }
-#pragma unroll
-    for (int k = 0; k < QR_NB; ++k) {
-        double s = 0.0;
-#pragma unroll
-        for (int l = 0; l < QR_NB; ++l) s = fma(p.t_transpose ? Ts[l][k] : Ts[k][l], w[l], s);
-        w2[k] = s;
-    }
+    for (int k = 0; k < QR_NB; ++k) w2[k] = (c < p.nc) ? p.w2[(size_t)k * p.nc + c] : 0.0;
     for (long long row0 = r_begin; row0 < r_end; row0 += QR_TR) {
         __syncthreads();
         stage_v(vt, p.V, row0, r_end);
@@ -337,6 +361,51 @@ __global__ void __launch_bounds__(256) qr_eye_kernel(double* Q, long long M, lon
     }
 }
 
+// ---- outer (BLAS-3) level: 128-column block reflector applied with the DMMA GEMM -------------
+constexpr int QR_NBO = 128;
+
+// Vx[i - J0][a] = V[i][a] for the JB reflectors starting at column/row J0 (explicit unit diagonal and zeros)
+__global__ void __launch_bounds__(256) qr_form_v_kernel(const double* __restrict__ A, long long lda, long long M,
+                                                        long long J0, int JB, double* Vx) {
+    const long long rows = M - J0, total = rows * QR_NBO;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / QR_NBO;
+        const int a = (int)(idx - r * QR_NBO);
+        double v = 0.0;
+        if (a < JB) {
+            if (r > a) v = A[(J0 + r) * lda + J0 + a];
+            else if (r == a) v = 1.0;
+        }
+        Vx[idx] = v;
+    }
+}
+
+// T (JB x JB upper, ld = QR_NBO) from the Gram matrix G = Vx^T Vx and tau (LAPACK dlarft, forward columnwise).
+__global__ void __launch_bounds__(QR_NBO) qr_build_tbig_kernel(const double* __restrict__ G, const double* __restrict__ tau,
+                                                               int JB, double* T) {
+    extern __shared__ double tb_smem[];
+    double* Ts = tb_smem;                       // [QR_NBO][QR_NBO + 1]
+    double* gcol = Ts + QR_NBO * (QR_NBO + 1);  // [QR_NBO]
+    const int r = threadIdx.x;
+    for (int c = 0; c < QR_NBO; ++c) Ts[r * (QR_NBO + 1) + c] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < JB; ++j) {
+        gcol[r] = (r < j) ? G[(size_t)r * QR_NBO + j] : 0.0;
+        __syncthreads();
+        const double tj = tau[j];
+        if (r < j) {
+            double sacc = 0.0;
+            for (int l = r; l < j; ++l) sacc = fma(Ts[r * (QR_NBO + 1) + l], gcol[l], sacc);
+            Ts[r * (QR_NBO + 1) + j] = -tj * sacc;
+        } else if (r == j) {
+            Ts[j * (QR_NBO + 1) + j] = tj;
+        }
+        __syncthreads();
+    }
+    for (int c = 0; c < QR_NBO; ++c) T[(size_t)r * QR_NBO + c] = Ts[r * (QR_NBO + 1) + c];
+}
+
 // ------------------------------------------------------------------------------------------ host side
 struct QrWs {
     unsigned int* counter;   // 64 B
@@ -345,7 +414,15 @@ struct QrWs {
     double* gram;            // sms * 256
     double* T;               // 256
     double* wpart;           // splits * 16 * ncols
+    double* w2;              // 16 * ncols
     int max_splits;
+    // outer (BLAS-3) level
+    double* Vx;              // (M) x 128   explicit block reflector
+    double* Gbig;            // 128 x 128
+    double* Tbig;            // 128 x 128
+    double* Wbig;            // 128 x N
+    double* W2big;           // 128 x N
+    void* gemm_ws; size_t gemm_ws_bytes;
 };
 
 static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
@@ -357,10 +434,19 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
     const size_t o_drow = take((size_t)2 * QR_NB * 8);
     const size_t o_gram = take((size_t)sms * QR_NB * QR_NB * 8);
     const size_t o_T = take(QR_NB * QR_NB * 8);
-    int max_splits = (int)((M + 255) / 256);
+    int max_splits = (int)((M + QR_TR - 1) / QR_TR);
     if (max_splits > 2 * sms) max_splits = 2 * sms;
     if (max_splits < 1) max_splits = 1;
     const size_t o_w = take((size_t)max_splits * QR_NB * (size_t)(N > 0 ? N : 1) * 8);
+    const size_t o_w2s = take((size_t)QR_NB * (size_t)(N > 0 ? N : 1) * 8);
+    const size_t o_vx = take((size_t)M * QR_NBO * 8);
+    const size_t o_gb = take((size_t)QR_NBO * QR_NBO * 8);
+    const size_t o_tb = take((size_t)QR_NBO * QR_NBO * 8);
+    const size_t o_wb = take((size_t)QR_NBO * (size_t)N * 8);
+    const size_t o_w2 = take((size_t)QR_NBO * (size_t)N * 8);
+    // split-K partials of the block-reflector GEMMs: at most 64 splits of a 128 x nc tile row (nc <= N)
+    const size_t gws = (size_t)64 * QR_NBO * (size_t)(N > QR_NBO ? N : QR_NBO) * 8;
+    const size_t o_gw = take(gws + 256);
     if (out) {
         char* b = (char*)base;
         out->counter = (unsigned int*)(b + o_counter);
@@ -369,7 +455,15 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
         out->gram = (double*)(b + o_gram);
         out->T = (double*)(b + o_T);
         out->wpart = (double*)(b + o_w);
+        out->w2 = (double*)(b + o_w2s);
         out->max_splits = max_splits;
+        out->Vx = (double*)(b + o_vx);
+        out->Gbig = (double*)(b + o_gb);
+        out->Tbig = (double*)(b + o_tb);
+        out->Wbig = (double*)(b + o_wb);
+        out->W2big = (double*)(b + o_w2);
+        out->gemm_ws = (void*)(b + o_gw);
+        out->gemm_ws_bytes = gws + 256;
     }
     return off;
 }
@@ -408,7 +502,7 @@ static int run_trailing(const double* Afac, long long lda, long long M, long lon
     const int sms = num_sms();
     const int col_blocks = (int)((nc + QR_THREADS - 1) / QR_THREADS);
     long long want = (2LL * sms + col_blocks - 1) / col_blocks;       // ~2 CTAs per SM
-    long long by_rows = (rows + 4 * QR_TR - 1) / (4 * QR_TR);         // >= 256 rows per split
+    long long by_rows = (rows + QR_TR - 1) / QR_TR;                   // >= 64 rows (one staged tile) per split
     int splits = (int)(want < by_rows ? want : by_rows);
     if (splits > w.max_splits) splits = w.max_splits;
     if (splits < 1) splits = 1;
@@ -416,9 +510,11 @@ static int run_trailing(const double* Afac, long long lda, long long M, long lon
     tp.V = VView{Afac, lda, j0, jb}; tp.M = M; tp.C = C; tp.ldc = ldc; tp.nc = nc;
     tp.rows_per_split = (rows + splits - 1) / splits;
     tp.splits = (int)((rows + tp.rows_per_split - 1) / tp.rows_per_split);
-    tp.wpart = w.wpart; tp.T = w.T; tp.t_transpose = t_transpose;
+    tp.wpart = w.wpart; tp.w2 = w.w2; tp.T = w.T; tp.t_transpose = t_transpose;
     dim3 grid(col_blocks, tp.splits);
     qr_trail_w_kernel<<<grid, QR_THREADS, 0, st>>>(tp);
+    PLA_LAUNCH_CHECK();
+    qr_trail_reduce_kernel<<<(unsigned)((nc + 31) / 32), QR_THREADS, 0, st>>>(tp);
     PLA_LAUNCH_CHECK();
     qr_trail_apply_kernel<<<grid, QR_THREADS, 0, st>>>(tp);
     PLA_LAUNCH_CHECK();
@@ -431,6 +527,40 @@ using namespace pla;
 
 extern "C" size_t pla_qr_workspace_bytes(int64_t M, int64_t N) { return qr_ws_layout(M, N, nullptr, nullptr); }
 
+// Build Vx (explicit reflectors J0 .. J0+JB-1) and the compact-WY factor Tbig of the whole block.
+static int build_block_reflector(const double* A, long long lda, long long M, long long J0, int JB,
+                                 const double* tau, const QrWs& w, cudaStream_t st) {
+    const long long rows = M - J0;
+    int nb = (int)((rows * QR_NBO + 255) / 256);
+    if (nb > 8 * num_sms()) nb = 8 * num_sms();
+    qr_form_v_kernel<<<nb, 256, 0, st>>>(A, lda, M, J0, JB, w.Vx);
+    PLA_LAUNCH_CHECK();
+    int rc = pla_gemm_f64(1, 0, QR_NBO, QR_NBO, rows, 1.0, w.Vx, QR_NBO, w.Vx, QR_NBO, 0.0, w.Gbig, QR_NBO,
+                          w.gemm_ws, w.gemm_ws_bytes, st);
+    if (rc) return rc;
+    const size_t smem = (size_t)(QR_NBO * (QR_NBO + 1) + QR_NBO) * sizeof(double);
+    PLA_CUDA(cudaFuncSetAttribute(qr_build_tbig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qr_build_tbig_kernel<<<1, QR_NBO, smem, st>>>(w.Gbig, tau + J0, JB, w.Tbig);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+// C[J0:M, 0:nc] <- (I - Vx op(Tbig) Vx^T) C  with three DMMA GEMMs
+static int apply_block_reflector(long long M, long long J0, double* C, long long ldc, long long nc, int t_transpose,
+                                 const QrWs& w, cudaStream_t st) {
+    if (nc <= 0) return 0;
+    const long long rows = M - J0;
+    double* Crows = C + J0 * ldc;
+    int rc = pla_gemm_f64(1, 0, QR_NBO, nc, rows, 1.0, w.Vx, QR_NBO, Crows, ldc, 0.0, w.Wbig, nc, w.gemm_ws,
+                          w.gemm_ws_bytes, st);                                   // W = Vx^T C
+    if (rc) return rc;
+    rc = pla_gemm_f64(t_transpose ? 1 : 0, 0, QR_NBO, nc, QR_NBO, 1.0, w.Tbig, QR_NBO, w.Wbig, nc, 0.0, w.W2big, nc,
+                      w.gemm_ws, w.gemm_ws_bytes, st);                            // W2 = op(T) W
+    if (rc) return rc;
+    return pla_gemm_f64(0, 0, rows, nc, QR_NBO, -1.0, w.Vx, QR_NBO, w.W2big, nc, 1.0, Crows, ldc, w.gemm_ws,
+                        w.gemm_ws_bytes, st);                                     // C -= Vx W2
+}
+
 extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64_t ncols_factor, double* tau,
                              void* ws, size_t ws_bytes, void* stream) {
     PLA_CHECK_ARG(A != nullptr, 1, "A is null");
@@ -442,13 +572,24 @@ extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64
     QrWs w;
     qr_ws_layout(M, N, ws, &w);
     cudaStream_t st = (cudaStream_t)stream;
-    for (long long j0 = 0; j0 < ncols_factor; j0 += QR_NB) {
-        const int jb = (int)((ncols_factor - j0) < QR_NB ? (ncols_factor - j0) : QR_NB);
-        int rc = run_panel(A, lda, M, j0, jb, tau, w, st);
-        if (rc) return rc;
-        const long long nc = N - (j0 + jb);
-        rc = run_trailing(A, lda, M, j0, jb, A + j0 + jb, lda, nc, /*T^T*/ 1, w, st);
-        if (rc) return rc;
+    for (long long J0 = 0; J0 < ncols_factor; J0 += QR_NBO) {
+        const int JB = (int)((ncols_factor - J0) < QR_NBO ? (ncols_factor - J0) : QR_NBO);
+        // inner level: 16-column panels; their reflectors are applied only inside this block
+        for (long long j0 = J0; j0 < J0 + JB; j0 += QR_NB) {
+            const int jb = (int)((J0 + JB - j0) < QR_NB ? (J0 + JB - j0) : QR_NB);
+            int rc = run_panel(A, lda, M, j0, jb, tau, w, st);
+            if (rc) return rc;
+            rc = run_trailing(A, lda, M, j0, jb, A + j0 + jb, lda, (J0 + JB) - (j0 + jb), /*T^T*/ 1, w, st);
+            if (rc) return rc;
+        }
+        // outer level: the whole block reflector hits the remaining columns through the tensor cores
+        const long long nc = N - (J0 + JB);
+        if (nc > 0) {
+            int rc = build_block_reflector(A, lda, M, J0, JB, tau, w, st);
+            if (rc) return rc;
+            rc = apply_block_reflector(M, J0, A + J0 + JB, lda, nc, /*T^T*/ 1, w, st);
+            if (rc) return rc;
+        }
     }
     return 0;
 }
@@ -466,20 +607,14 @@ extern "C" int pla_orgqr_f64(const double* A, int64_t M, int64_t K, int64_t lda,
     const int sms = num_sms();
     qr_eye_kernel<<<4 * sms, 256, 0, st>>>(Q, M, K, ldq);
     PLA_LAUNCH_CHECK();
-    // Q = H_1 H_2 ... H_p [I; 0]: apply the panels last to first; panel j0 only touches columns >= j0
-    const long long last = ((K - 1) / QR_NB) * QR_NB;
-    for (long long j0 = last; j0 >= 0; j0 -= QR_NB) {
-        const int jb = (int)((K - j0) < QR_NB ? (K - j0) : QR_NB);
-        VView V{A, lda, j0, jb};
-        const long long rows = M - j0;
-        int GG = (int)((rows + 4 * QR_TR - 1) / (4 * QR_TR));
-        if (GG > sms) GG = sms;
-        if (GG < 1) GG = 1;
-        qr_gram_kernel<<<GG, QR_THREADS, 0, st>>>(V, M, (rows + GG - 1) / GG, w.gram);
-        PLA_LAUNCH_CHECK();
-        qr_build_t_kernel<<<1, QR_THREADS, 0, st>>>(w.gram, GG, tau + j0, jb, w.T);
-        PLA_LAUNCH_CHECK();
-        int rc = run_trailing(A, lda, M, j0, jb, Q + j0, ldq, K - j0, /*T*/ 0, w, st);
+    // Q = H_1 H_2 ... H_K [I; 0]: apply the 128-column block reflectors last to first; block J0 only
+    // touches rows >= J0 and columns >= J0
+    const long long last = ((K - 1) / QR_NBO) * QR_NBO;
+    for (long long J0 = last; J0 >= 0; J0 -= QR_NBO) {
+        const int JB = (int)((K - J0) < QR_NBO ? (K - J0) : QR_NBO);
+        int rc = build_block_reflector(A, lda, M, J0, JB, tau, w, st);
+        if (rc) return rc;
+        rc = apply_block_reflector(M, J0, Q + J0, ldq, K - J0, /*T*/ 0, w, st);
         if (rc) return rc;
     }
     return 0;

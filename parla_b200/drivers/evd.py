@@ -2,8 +2,11 @@
 ``EVD1`` (:211-289; A symmetric)."""
 import numpy as np
 import torch
+import torch.distributed
 
+from .. import distla
 from .. import kernels as K
+from ..parallel import RowSharded, allreduce_
 from ..comps.qb import QBDecomposer
 
 
@@ -30,7 +33,12 @@ class EVD1(EVDecomposer):
             assert tol < np.inf
         rng = np.random.default_rng(rng)
         Q, B = self.qb(A, k + over, tol / 2, rng)                  # :276
-        C = K.gemm(B, Q)                                           # :278
+        if isinstance(Q, RowSharded):                              # B replicated (k x n), Q row-sharded (n x k)
+            lo = Q.row_offset
+            C = K.gemm(B[:, lo:lo + Q.local.shape[0]], Q.local)
+            allreduce_(C, Q.group if Q.group is not None else torch.distributed.group.WORLD)
+        else:
+            C = K.gemm(B, Q)                                       # :278
         lamb, U = torch.linalg.eigh(C)                             # :279 small dense: cuSOLVER glue
         alamb = torch.abs(lamb)
         d = Q.shape[1]
@@ -38,7 +46,7 @@ class EVD1(EVDecomposer):
         I = torch.argsort(-alamb, stable=True)[:r]                 # :284
         U = U[:, I]
         lamb = lamb[I]
-        V = K.gemm(Q, U)                                           # :288
+        V = distla.mm(Q, U.contiguous())                           # :288
         return V, lamb
 
     exec = __call__

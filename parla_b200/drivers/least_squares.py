@@ -95,9 +95,13 @@ def _sketch(sketch_op_gen, d, A, b, delta, rng):
     if S.shape[1] != A_loc.shape[0]:           # a full-width operator (e.g. a replayed reference S)
         S = S.column_slice(row_off, A_loc.shape[0])
     d_aug = d + (n if delta > 0 else 0)
-    W = torch.empty(d_aug, n + 1, dtype=F64, device=A_loc.device)
+    # even leading dimension (16-byte aligned rows) so the QR's tensor-core trailing updates and
+    # the sketch kernels can use vector accesses; the pad column is kept at zero
+    ld = n + 1 + ((n + 1) % 2)
+    Wfull = torch.zeros(d_aug, ld, dtype=F64, device=A_loc.device)
+    W = Wfull[:, :n + 1]
     S.sketch_into(A_loc, b_loc, W[:d], row_offset=row_off)
-    allreduce_(W[:d], group)
+    allreduce_(Wfull[:d], group)
     if delta > 0:
         W[d:, :].zero_()
         W[d:, :n].diagonal().fill_(math.sqrt(delta))

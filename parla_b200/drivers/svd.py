@@ -2,7 +2,7 @@
 import numpy as np
 import torch
 
-from .. import kernels as K
+from .. import distla
 from ..comps.qb import QBDecomposer
 
 
@@ -31,7 +31,7 @@ class SVD1(SVDecomposer):
         if bool(drop.any()):
             keep = ~drop
             U, s, Vh = U[:, keep], s[keep], Vh[keep, :]
-        U = K.gemm(Q, U)                                           # :175
+        U = distla.mm(Q, U.contiguous())                           # :175
         return U, s, Vh
 
     exec = __call__

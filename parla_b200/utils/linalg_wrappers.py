@@ -1,6 +1,7 @@
-"""parla/utils/linalg_wrappers.py:6-7 on the device: ``orth`` = Q factor of an economic Householder QR."""
-from .. import kernels as K
+"""parla/utils/linalg_wrappers.py:6-7 on the device: ``orth`` = Q factor of an economic Householder QR
+(a Householder TSQR when the argument is ``RowSharded``)."""
+from .. import distla
 
 
 def orth(S):
-    return K.qr_economic(S)[0]
+    return distla.orth(S)

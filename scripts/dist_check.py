@@ -1,0 +1,88 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the row-sharded drivers must
+reproduce the single-GPU results on the same global problem.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dist_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import parla_b200 as rla                      # noqa: E402
+from oracle import parla_oracle as orc        # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ok = True
+
+    def report(name, err, tol):
+        nonlocal ok
+        good = err <= tol
+        ok = ok and good
+        if rank == 0:
+            print(f"{'OK  ' if good else 'FAIL'} {name:58s} {err:.3e} (tol {tol:.0e})", flush=True)
+
+    # ---------------- least squares: same global (A, b) on every rank, rows split evenly
+    rng = np.random.default_rng(0)
+    m, n = 4096 * world, 200
+    A = rng.standard_normal((m, n)) * np.logspace(0, 2, n)
+    b = A @ rng.standard_normal(n) + 0.1 * rng.standard_normal(m)
+    Ad, bd = torch.from_numpy(A).to(dev), torch.from_numpy(b).to(dev)
+    mine = slice(rank * (m // world), (rank + 1) * (m // world))
+    Ash = rla.RowSharded.from_rank(Ad[mine].contiguous())
+    bsh = rla.RowSharded.from_rank(bd[mine].contiguous())
+    for gen_name, gen in (("SkOpGA", rla.SkOpGA()), ("SkOpSJ", rla.SkOpSJ(8))):
+        for mode, delta in (("qr", 0.0), ("svd", 0.0), ("qr", 0.3)):
+            x1, log1 = rla.SPO(gen, 4, mode)(Ad, bd, delta, 1e-12, 100, 5)
+            xs, logs = rla.SPO(gen, 4, mode)(Ash, bsh, delta, 1e-12, 100, 5)
+            err = float(torch.linalg.vector_norm(xs - x1) / torch.linalg.vector_norm(x1))
+            report(f"SPO[{gen_name},{mode},delta={delta}] sharded vs 1 GPU, {logs.iters}/{log1.iters} its", err, 1e-10)
+    S = orc.sjlt_operator(4 * n, m, np.random.default_rng(3), 8)          # replayed reference operator
+    x_ref, _ = orc.SPO(lambda d, mm, r: S, 4, 'qr')(A, b, 0.0, 1e-12, 100, None)
+    xs, _ = rla.SPO(lambda d, mm, r: S, 4, 'qr')(Ash, bsh, 0.0, 1e-12, 100, None)
+    report("SPO[replayed scipy SJLT] sharded vs oracle", float(np.linalg.norm(xs.cpu().numpy() - x_ref) / np.linalg.norm(x_ref)), 1e-10)
+
+    # ---------------- low rank: SVD1 over QB1 / QB2, numpy test matrices replayed (identical on both paths)
+    A2 = orc.exponent_spectrum(2048 * world, 300, 120, np.random.default_rng(1), 8.0)
+    A2d = torch.from_numpy(A2).to(dev)
+    mine2 = slice(rank * 2048, (rank + 1) * 2048)
+    for name, mk in (("QB1", lambda: rla.QB1(rla.RF1(rla.RS1(orc.SkOpGA(), 2, rla.orth, 1)))),
+                     ("QB2", lambda: rla.QB2(rla.RF1(rla.RS1(orc.SkOpGA(), 2, rla.orth, 1)), 16, False)),
+                     ("QB1 odd passes, native S", lambda: rla.QB1(rla.RF1(rla.RS1(rla.SkOpGA(), 3, rla.orth, 1))))):
+        U1, s1, V1 = rla.SVD1(mk())(A2d, 40, 0.0 if name == "QB2" else np.nan, 0, 7)
+        A2sh = rla.RowSharded.from_rank(A2d[mine2].contiguous())
+        Us, ss, Vs = rla.SVD1(mk())(A2sh, 40, 0.0 if name == "QB2" else np.nan, 0, 7)
+        report(f"SVD1[{name}] singular values sharded vs 1 GPU", float((ss - s1).abs().max() / s1[0]), 1e-10)
+        ap1 = (U1 * s1) @ V1
+        aps = (Us.local * ss) @ Vs
+        report(f"SVD1[{name}] U s V^T (local rows) sharded vs 1 GPU", float(torch.linalg.norm(aps - ap1[mine2]) / torch.linalg.norm(ap1)), 1e-10)
+        G = Us.local.T @ Us.local
+        dist.all_reduce(G)
+        report(f"SVD1[{name}] |U^T U - I| of the sharded U", float(torch.linalg.norm(G - torch.eye(G.shape[0], device=dev, dtype=G.dtype))), 1e-10)
+    # symmetric EVD
+    H = A2[:300 * 1].T @ A2[:300]
+    nH = (H.shape[0] // world) * world
+    H = 0.5 * (H + H.T)[:nH, :nH]
+    Hd = torch.from_numpy(np.ascontiguousarray(H)).to(dev)
+    V1, l1 = rla.EVD1(rla.QB1(rla.RF1(rla.RS1(orc.SkOpGA(), 2, rla.orth, 1))))(Hd, 20, np.nan, 5, 3)
+    mineH = slice(rank * (nH // world), (rank + 1) * (nH // world))
+    Vs, ls = rla.EVD1(rla.QB1(rla.RF1(rla.RS1(orc.SkOpGA(), 2, rla.orth, 1))))(rla.RowSharded.from_rank(Hd[mineH].contiguous()), 20, np.nan, 5, 3)
+    report("EVD1 eigenvalues sharded vs 1 GPU", float((ls - l1).abs().max() / l1.abs().max()), 1e-10)
+
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if float(flag) == 1.0 else "FAIL", f"world={world}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if float(flag) == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
