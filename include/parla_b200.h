@@ -116,14 +116,15 @@ int pla_lsqr_ridge_f64(int64_t n, double sd, const double* xw, double* ub, const
  * Replaces `S @ A` for the scipy CSC operator of parla/utils/sketching.py:51-74 applied at
  * parla/drivers/least_squares.py:303,314 (scipy.sparse csc_matvecs).
  * S is d x m with exactly k nonzeros per column, values sign/sqrt(k).
- *   pla_sjlt_plan_f64: builds the destination-major (CSR) plan from the index form
+ *   pla_sjlt_plan_f64: builds the destination-major plan from the index form
  *       rows[m*k] (int32, row index of the q-th nonzero of column i at rows[i*k+q]),
- *       signs[m*k] (int8, +1/-1).  plan: d+1 offsets (int64) followed by m*k packed entries (int32:
- *       source row * 2 + (sign < 0)), within each destination ordered by source row (deterministic).
+ *       signs[m*k] (int8, +1/-1).  plan: header, bucket offsets (int64) and m*k packed entries (int32:
+ *       source row * 2 + (sign < 0)); bucket (r, w) = nonzeros of destination r with source row in
+ *       window w (<= 2^16 rows), each bucket ordered by source row (deterministic summation order).
  *   pla_sjlt_apply_f64: out[d x n] (+)= scale * S @ A,  accumulate = 0 overwrites; when bvec != NULL
  *       also out_b[r * ldob] (+)= scale * (S @ bvec)[r] (the `S @ b` of least_squares.py:314) in the same launch.
- *   Segments longer than 8192 entries per destination row are left in arrival order (the sum is then
- *   correct but its rounding is not run-to-run reproducible).                                      */
+ *   Buckets longer than 8192 entries (only possible for extreme m*k/d) are left in arrival order: the
+ *   sum is then correct but its rounding is not run-to-run reproducible.                           */
 size_t pla_sjlt_plan_bytes(int64_t d, int64_t m, int64_t k);
 size_t pla_sjlt_plan_workspace_bytes(int64_t d, int64_t m, int64_t k);
 int pla_sjlt_plan_f64(const int32_t* rows, const int8_t* signs, int64_t m, int64_t k, int64_t d, void* plan,

@@ -3,13 +3,13 @@
 // Replaces scipy.sparse csc_matvecs behind `S @ A` / `S @ b` (parla/drivers/least_squares.py:303,314)
 // for the operator built by parla/utils/sketching.py:51-74.
 //
-// Formulation: destination-major gather.  A one-off plan turns the column-wise index form into CSR
-// (per destination row: the list of (source row, sign), sorted by source row).  One warp then owns
+// Formulation: destination-major gather.  A one-off plan turns the column-wise index form into
+// buckets (destination row, window of 2^16 source rows), each sorted by source row.  One warp owns
 // (destination row, 256-column chunk): it walks its list, reads 2 KB contiguous pieces of the source
-// rows (coalesced), accumulates in registers and writes each output element exactly once -- no
-// atomics, no shared-memory read-modify-write, fixed summation order (deterministic).  Tasks are
-// ordered chunk-major and every list is sorted by source row, so the k readers of a source-row piece
-// run close together in time and share it through the 126 MB L2.
+// rows (coalesced), accumulates in registers and adds into the output once per launch -- no atomics,
+// no shared-memory read-modify-write, fixed summation order (deterministic).  The apply is issued as
+// one launch per source window, so at any time all warps read the same ~1 GB slice of A: the k readers
+// of a source-row piece then mostly hit it in the 126 MB L2 / TLB instead of re-reading HBM.
 #include "common.cuh"
 #include "philox.cuh"
 #include "../../include/parla_b200.h"
@@ -19,14 +19,35 @@ namespace pla {
 constexpr long long SJ_MAGIC = 0x504C41534A4C5431LL;   // "PLASJLT1"
 constexpr int SJ_SORT_MAX = 8192;                      // per-destination segment sorted in smem up to this
 
-struct SjltPlanHeader { long long magic, nnz, bad_index_count, pad; };
+// Plan layout: header | boff[d * nwin + 1] (int64) | entries[nnz] (int32, (src << 1) | negative).
+// Bucket (r, w) = nonzeros of destination row r whose source row lies in window w (win_rows = 1 << win_shift
+// consecutive rows of A); buckets are stored r-major, so destination r's full list is the concatenation of
+// its windows in source order, and every bucket is sorted by source row (deterministic summation order).
+struct SjltPlanHeader { long long magic, nnz, bad_index_count, nwin, win_shift, pad0, pad1, pad2; };
 
-__global__ void __launch_bounds__(256) sjlt_count_kernel(const int32_t* __restrict__ rows, long long nnz, long long d,
+static int sjlt_win_shift(long long d, long long k) {
+    // windows of <= 2^16 source rows (~1 GB of A at n = 2048: bounded TLB / L2 footprint per launch;
+    // measured on B200: 72 ms un-windowed -> 49 ms at 2^22 x 2048, flat below 2^16) and
+    // <= ~4096 expected entries per bucket (sorted in shared memory)
+    long long lim = 4096 * d / (k > 0 ? k : 1);
+    static int max_shift = 0;
+    if (max_shift == 0) {
+        const char* e = getenv("PLA_SJLT_WIN_SHIFT");
+        max_shift = e ? atoi(e) : 16;
+        if (max_shift < 10 || max_shift > 24) max_shift = 16;
+    }
+    int sh = max_shift;
+    while (sh > 10 && (1LL << sh) > lim) --sh;
+    return sh;
+}
+
+__global__ void __launch_bounds__(256) sjlt_count_kernel(const int32_t* __restrict__ rows, long long nnz, long long k,
+                                                         long long d, long long nwin, int win_shift,
                                                          unsigned long long* counts, SjltPlanHeader* hdr) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
         const long long r = rows[e];
         if (r < 0 || r >= d) atomicAdd((unsigned long long*)&hdr->bad_index_count, 1ULL);
-        else atomicAdd(&counts[r], 1ULL);
+        else atomicAdd(&counts[r * nwin + ((e / k) >> win_shift)], 1ULL);
     }
 }
 
@@ -69,15 +90,16 @@ __global__ void __launch_bounds__(1024) sjlt_scan_kernel(const unsigned long lon
 }
 
 __global__ void __launch_bounds__(256) sjlt_fill_kernel(const int32_t* __restrict__ rows, const int8_t* __restrict__ signs,
-                                                        long long nnz, long long k, long long d,
-                                                        const long long* __restrict__ offsets,
+                                                        long long nnz, long long k, long long d, long long nwin,
+                                                        int win_shift, const long long* __restrict__ boff,
                                                         unsigned long long* cursor, int32_t* entries) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x) {
         const long long r = rows[e];
         if (r < 0 || r >= d) continue;
         const long long src = e / k;
-        const unsigned long long slot = atomicAdd(&cursor[r], 1ULL);
-        entries[offsets[r] + (long long)slot] = (int32_t)((src << 1) | (signs[e] < 0 ? 1 : 0));
+        const long long bkt = r * nwin + (src >> win_shift);
+        const unsigned long long slot = atomicAdd(&cursor[bkt], 1ULL);
+        entries[boff[bkt] + (long long)slot] = (int32_t)((src << 1) | (signs[e] < 0 ? 1 : 0));
     }
 }
 
@@ -106,31 +128,33 @@ __global__ void __launch_bounds__(256) sjlt_segsort_kernel(const long long* __re
     for (int i = threadIdx.x; i < len; i += blockDim.x) entries[beg + i] = seg[i];
 }
 
-// ---- apply: warp <-> (destination row, column chunk of 32*VEC*J columns)
-template <int VEC, int J>
-__global__ void __launch_bounds__(256) sjlt_apply_kernel(const long long* __restrict__ offsets,
-                                                         const int32_t* __restrict__ entries, long long d,
-                                                         const double* __restrict__ A, long long n, long long lda,
-                                                         const double* __restrict__ bvec, double scale, double* out,
-                                                         long long ldo, double* out_b, long long ldob,
-                                                         int accumulate, long long nchunks, int splits,
-                                                         double* part) {
+// ---- apply: warp <-> (DPW consecutive destination rows, column chunk of 32*VEC*J columns)
+// All destination rows of a chunk should be co-resident on the GPU: their (source-sorted) lists are
+// then swept in step, so the k readers of a source-row piece hit it in L2 and A is read from HBM about
+// once.  DPW > 1 (several lists interleaved per warp, batch by batch) and narrower chunks trade
+// accumulator registers for that co-residency when d is large.
+template <int VEC, int J, int DPW>
+__global__ void __launch_bounds__(256, 4) sjlt_apply_kernel(const long long* __restrict__ offsets,
+                                                            const int32_t* __restrict__ entries, long long d,
+                                                            const double* __restrict__ A, long long n, long long lda,
+                                                            const double* __restrict__ bvec, double scale, double* out,
+                                                            long long ldo, double* out_b, long long ldob,
+                                                            int accumulate, long long nchunks, int splits,
+                                                            double* part, long long nwin, long long w_lo,
+                                                            long long w_hi) {
     // splits > 1: every destination list is cut into `splits` segments handled by different warps
     // (more parallelism when d * n is small); segment sums go to part[seg][d][n+1] and are added in
     // segment order by sjlt_reduce_kernel.
     constexpr int CW = 32 * VEC * J;                    // chunk width in columns
     const int lane = threadIdx.x & 31;
+    const long long dgroups = (d + DPW - 1) / DPW;
     const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (task >= nchunks * d * splits) return;
+    if (task >= nchunks * dgroups * splits) return;
     const int seg = (int)(task % splits);
     const long long cr = task / splits;
-    const long long chunk = cr / d, r = cr - chunk * d;
+    const long long chunk = cr / dgroups, r0 = (cr - chunk * dgroups) * DPW;
     const long long c0 = chunk * CW;
-    long long beg = offsets[r], end = offsets[r + 1];
     if (splits > 1) {
-        const long long len = end - beg;
-        const long long b2 = beg + len * seg / splits, e2 = beg + len * (seg + 1) / splits;
-        beg = b2; end = e2;
         out = part + (size_t)seg * d * (n + 1);
         ldo = n + 1;
         out_b = (bvec != nullptr) ? out + n : nullptr;
@@ -138,54 +162,82 @@ __global__ void __launch_bounds__(256) sjlt_apply_kernel(const long long* __rest
         accumulate = 0;
         scale = 1.0;
     }
-    double acc[J * VEC];
+    long long pos[DPW], end[DPW];
+    double acc[DPW][J * VEC], bacc[DPW];
 #pragma unroll
-    for (int j = 0; j < J * VEC; ++j) acc[j] = 0.0;
-    double bacc = 0.0;
+    for (int p = 0; p < DPW; ++p) {
+        const long long r = r0 + p;
+        long long b0 = 0, e0 = 0;
+        if (r < d) {
+            b0 = offsets[r * nwin + w_lo];          // buckets (r, w_lo) .. (r, w_hi - 1) are contiguous
+            e0 = offsets[r * nwin + w_hi];
+            if (splits > 1) {
+                const long long len = e0 - b0;
+                const long long b2 = b0 + len * seg / splits, e2 = b0 + len * (seg + 1) / splits;
+                b0 = b2; e0 = e2;
+            }
+        }
+        pos[p] = b0; end[p] = e0; bacc[p] = 0.0;
+#pragma unroll
+        for (int j = 0; j < J * VEC; ++j) acc[p][j] = 0.0;
+    }
     const bool do_b = (bvec != nullptr) && (chunk == 0);
 
-    for (long long e0 = beg; e0 < end; e0 += 32) {
-        const long long me = e0 + lane;
-        const int32_t ent = me < end ? entries[me] : 0;
-        if (do_b && me < end) {
-            const double bv = bvec[ent >> 1];
-            bacc += (ent & 1) ? -bv : bv;
-        }
-        const int cnt = (int)min(32LL, end - e0);
-#pragma unroll 4
-        for (int t = 0; t < cnt; ++t) {
-            const int32_t en = __shfl_sync(0xffffffffu, ent, t);
-            const double* src = A + (long long)(en >> 1) * lda + c0;
-            const double sg = (en & 1) ? -1.0 : 1.0;
+    bool any = true;
+    while (any) {
+        any = false;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const long long c = (long long)VEC * (lane + 32 * j);
-                if (c0 + c < n) {
-                    if (VEC == 2) {
-                        const double2 a = __ldg(reinterpret_cast<const double2*>(src + c));
-                        acc[j * VEC] = fma(sg, a.x, acc[j * VEC]);
-                        acc[j * VEC + VEC - 1] = fma(sg, a.y, acc[j * VEC + VEC - 1]);
-                    } else {
-                        acc[j * VEC] = fma(sg, __ldg(src + c), acc[j * VEC]);
+        for (int p = 0; p < DPW; ++p) {
+            if (pos[p] >= end[p]) continue;            // warp-uniform
+            const long long me = pos[p] + lane;
+            const int32_t ent = me < end[p] ? entries[me] : 0;
+            if (do_b && me < end[p]) {
+                const double bv = bvec[ent >> 1];
+                bacc[p] += (ent & 1) ? -bv : bv;
+            }
+            const int cnt = (int)min(32LL, end[p] - pos[p]);
+#pragma unroll 2
+            for (int t = 0; t < cnt; ++t) {
+                const int32_t en = __shfl_sync(0xffffffffu, ent, t);
+                const double* src = A + (long long)(en >> 1) * lda + c0;
+                const double sg = (en & 1) ? -1.0 : 1.0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const long long c = (long long)VEC * (lane + 32 * j);
+                    if (c0 + c < n) {
+                        if (VEC == 2) {
+                            const double2 a = __ldg(reinterpret_cast<const double2*>(src + c));
+                            acc[p][j * VEC] = fma(sg, a.x, acc[p][j * VEC]);
+                            acc[p][j * VEC + VEC - 1] = fma(sg, a.y, acc[p][j * VEC + VEC - 1]);
+                        } else {
+                            acc[p][j * VEC] = fma(sg, __ldg(src + c), acc[p][j * VEC]);
+                        }
                     }
                 }
             }
+            pos[p] += 32;
+            any = any || (pos[p] < end[p]);
         }
     }
-    double* dst = out + r * ldo + c0;
 #pragma unroll
-    for (int j = 0; j < J; ++j)
+    for (int p = 0; p < DPW; ++p) {
+        const long long r = r0 + p;
+        if (r >= d) continue;
+        double* dst = out + r * ldo + c0;
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            const long long c = (long long)VEC * (lane + 32 * j) + v;
-            if (c0 + c < n) {
-                const double val = scale * acc[j * VEC + v];
-                dst[c] = accumulate ? dst[c] + val : val;
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const long long c = (long long)VEC * (lane + 32 * j) + v;
+                if (c0 + c < n) {
+                    const double val = scale * acc[p][j * VEC + v];
+                    dst[c] = accumulate ? dst[c] + val : val;
+                }
             }
+        if (do_b && out_b != nullptr) {
+            const double tot = warp_sum(bacc[p]);
+            if (lane == 0) out_b[r * ldob] = accumulate ? out_b[r * ldob] + scale * tot : scale * tot;
         }
-    if (do_b && out_b != nullptr) {
-        bacc = warp_sum(bacc);
-        if (lane == 0) out_b[r * ldob] = accumulate ? out_b[r * ldob] + scale * bacc : scale * bacc;
     }
 }
 
@@ -245,12 +297,17 @@ using namespace pla;
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+static long long sjlt_nwin(long long d, long long m, long long k) {
+    const int sh = sjlt_win_shift(d, k);
+    return (m + (1LL << sh) - 1) >> sh;
+}
+
 extern "C" size_t pla_sjlt_plan_bytes(int64_t d, int64_t m, int64_t k) {
-    return align256(sizeof(SjltPlanHeader)) + align256((size_t)(d + 1) * 8) + align256((size_t)m * k * 4);
+    return align256(sizeof(SjltPlanHeader)) + align256((size_t)(d * sjlt_nwin(d, m, k) + 1) * 8) +
+           align256((size_t)m * k * 4);
 }
 extern "C" size_t pla_sjlt_plan_workspace_bytes(int64_t d, int64_t m, int64_t k) {
-    (void)m; (void)k;
-    return 2 * align256((size_t)d * 8);
+    return 2 * align256((size_t)d * sjlt_nwin(d, m, k) * 8);
 }
 
 extern "C" int pla_sjlt_plan_f64(const int32_t* rows, const int8_t* signs, int64_t m, int64_t k, int64_t d,
@@ -262,45 +319,60 @@ extern "C" int pla_sjlt_plan_f64(const int32_t* rows, const int8_t* signs, int64
     PLA_CHECK_ARG(plan != nullptr, 6, "plan is null");
     PLA_CHECK_ARG(ws != nullptr && ws_bytes >= pla_sjlt_plan_workspace_bytes(d, m, k), 8, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    const int win_shift = sjlt_win_shift(d, k);
+    const long long nwin = sjlt_nwin(d, m, k), nb_total = d * nwin;
     char* pb = (char*)plan;
     SjltPlanHeader* hdr = (SjltPlanHeader*)pb;
-    long long* offsets = (long long*)(pb + align256(sizeof(SjltPlanHeader)));
-    int32_t* entries = (int32_t*)(pb + align256(sizeof(SjltPlanHeader)) + align256((size_t)(d + 1) * 8));
+    long long* boff = (long long*)(pb + align256(sizeof(SjltPlanHeader)));
+    int32_t* entries = (int32_t*)(pb + align256(sizeof(SjltPlanHeader)) + align256((size_t)(nb_total + 1) * 8));
     unsigned long long* counts = (unsigned long long*)ws;
-    unsigned long long* cursor = (unsigned long long*)((char*)ws + align256((size_t)d * 8));
+    unsigned long long* cursor = (unsigned long long*)((char*)ws + align256((size_t)nb_total * 8));
     const long long nnz = m * k;
-    SjltPlanHeader h{SJ_MAGIC, nnz, 0, 0};
+    SjltPlanHeader h{SJ_MAGIC, nnz, 0, nwin, win_shift, 0, 0, 0};
     PLA_CUDA(cudaMemcpyAsync(hdr, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-    PLA_CUDA(cudaMemsetAsync(ws, 0, 2 * align256((size_t)d * 8), st));
+    PLA_CUDA(cudaMemsetAsync(ws, 0, 2 * align256((size_t)nb_total * 8), st));
     int nb = (int)((nnz + 255) / 256);
     if (nb > 16 * num_sms()) nb = 16 * num_sms();
-    sjlt_count_kernel<<<nb, 256, 0, st>>>(rows, nnz, d, counts, hdr);
+    sjlt_count_kernel<<<nb, 256, 0, st>>>(rows, nnz, k, d, nwin, win_shift, counts, hdr);
     PLA_LAUNCH_CHECK();
-    sjlt_scan_kernel<<<1, 1024, 0, st>>>(counts, d, offsets);
+    sjlt_scan_kernel<<<1, 1024, 0, st>>>(counts, nb_total, boff);
     PLA_LAUNCH_CHECK();
-    sjlt_fill_kernel<<<nb, 256, 0, st>>>(rows, signs, nnz, k, d, offsets, cursor, entries);
+    sjlt_fill_kernel<<<nb, 256, 0, st>>>(rows, signs, nnz, k, d, nwin, win_shift, boff, cursor, entries);
     PLA_LAUNCH_CHECK();
     PLA_CUDA(cudaFuncSetAttribute(sjlt_segsort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SJ_SORT_MAX * 4));
-    sjlt_segsort_kernel<<<(unsigned)d, 256, SJ_SORT_MAX * 4, st>>>(offsets, entries);
+    sjlt_segsort_kernel<<<(unsigned)nb_total, 256, SJ_SORT_MAX * 4, st>>>(boff, entries);
     PLA_LAUNCH_CHECK();
     return 0;
 }
 
-static int sjlt_splits(long long d, long long nchunks, long long n, size_t ws_bytes) {
-    const long long warps = d * nchunks, want = 4LL * num_sms() * 8;
+// Launch shape: chunk width (32*VEC*J columns) and destinations per warp (DPW) chosen so that one
+// chunk's d / DPW warps fit among the ~32 resident warps per SM; few warps overall -> split the lists.
+struct SjltShape { int J, DPW; long long cw, nchunks, dgroups; int splits; };
+
+static SjltShape sjlt_shape(long long d, long long n, int vec, size_t ws_bytes, bool have_ws) {
+    const long long resident = (long long)num_sms() * 32;
+    SjltShape sh;
+    sh.J = 4; sh.DPW = 1;                       // measured best on B200; (J=2,DPW=2) / (J=1,DPW=4) via env
+    if (const char* e = getenv("PLA_SJLT_DPW")) {
+        const int v = atoi(e);
+        if (v == 2) { sh.J = 2; sh.DPW = 2; } else if (v == 4) { sh.J = 1; sh.DPW = 4; }
+    }
+    (void)resident;
+    sh.cw = 32LL * vec * sh.J;
+    sh.nchunks = (n + sh.cw - 1) / sh.cw;
+    sh.dgroups = (d + sh.DPW - 1) / sh.DPW;
+    const long long warps = sh.dgroups * sh.nchunks, want = resident;
     long long sp = (want + warps - 1) / warps;
     if (sp > 16) sp = 16;
-    const long long fit = (long long)(ws_bytes / ((size_t)d * (size_t)(n + 1) * 8));
+    const long long fit = have_ws ? (long long)(ws_bytes / ((size_t)d * (size_t)(n + 1) * 8)) : 0;
     if (sp > fit) sp = fit;
-    return sp < 2 ? 1 : (int)sp;
+    sh.splits = sp < 2 ? 1 : (int)sp;
+    return sh;
 }
 
 extern "C" size_t pla_sjlt_apply_workspace_bytes(int64_t d, int64_t n) {
-    const long long nchunks = (n + 255) / 256;
-    const long long warps = d * nchunks, want = 4LL * num_sms() * 8;
-    long long sp = (want + warps - 1) / warps;
-    if (sp > 16) sp = 16;
-    return sp < 2 ? 0 : (size_t)sp * d * (n + 1) * 8;
+    const SjltShape sh = sjlt_shape(d, n, (n % 2 == 0) ? 2 : 1, ~(size_t)0, true);
+    return sh.splits < 2 ? 0 : (size_t)sh.splits * d * (n + 1) * 8;
 }
 
 extern "C" int pla_sjlt_apply_f64(const void* plan, int64_t d, int64_t m, int64_t k, const double* A, int64_t n,
@@ -312,30 +384,52 @@ extern "C" int pla_sjlt_apply_f64(const void* plan, int64_t d, int64_t m, int64_
     PLA_CHECK_ARG(A != nullptr && n >= 1 && lda >= n, 5, "bad A / n / lda");
     PLA_CHECK_ARG(out != nullptr && ldo >= n, 10, "bad out / ldo");
     PLA_CHECK_ARG(bvec == nullptr || (out_b != nullptr && ldob >= 1), 12, "out_b is null / ldob < 1");
+    const long long nwin = sjlt_nwin(d, m, k), nb_total = d * nwin;
     const char* pb = (const char*)plan;
     const long long* offsets = (const long long*)(pb + align256(sizeof(SjltPlanHeader)));
-    const int32_t* entries = (const int32_t*)(pb + align256(sizeof(SjltPlanHeader)) + align256((size_t)(d + 1) * 8));
+    const int32_t* entries = (const int32_t*)(pb + align256(sizeof(SjltPlanHeader)) + align256((size_t)(nb_total + 1) * 8));
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec2 = (n % 2 == 0) && (lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const SjltShape sh = sjlt_shape(d, n, vec2 ? 2 : 1, ws_bytes, ws != nullptr);
     const int warps_per_cta = 8;
-    const long long cw = vec2 ? 256 : 128, nchunks = (n + cw - 1) / cw;
-    const int splits = (ws != nullptr) ? sjlt_splits(d, nchunks, n, ws_bytes) : 1;
-    const long long ctas = (nchunks * d * splits + warps_per_cta - 1) / warps_per_cta;
-    double* part = splits > 1 ? (double*)ws : nullptr;
-    if (vec2)
-        sjlt_apply_kernel<2, 4><<<(unsigned)ctas, 256, 0, st>>>(offsets, entries, d, A, n, lda, bvec, scale, out, ldo,
-                                                               out_b, ldob, accumulate, nchunks, splits, part);
-    else
-        sjlt_apply_kernel<1, 4><<<(unsigned)ctas, 256, 0, st>>>(offsets, entries, d, A, n, lda, bvec, scale, out, ldo,
-                                                               out_b, ldob, accumulate, nchunks, splits, part);
-    PLA_LAUNCH_CHECK();
-    if (splits > 1) {
-        long long total = d * (n + 1);
-        int nb = (int)((total + 255) / 256);
-        if (nb > 8 * num_sms()) nb = 8 * num_sms();
-        sjlt_reduce_kernel<<<nb, 256, 0, st>>>(part, splits, d, n, bvec != nullptr ? 1 : 0, scale, out, ldo, out_b,
-                                               ldob, accumulate);
+    const long long ctas = (sh.nchunks * sh.dgroups * sh.splits + warps_per_cta - 1) / warps_per_cta;
+    double* part = sh.splits > 1 ? (double*)ws : nullptr;
+    // One launch per group of source windows: every launch only touches a few GB of A, and the output
+    // is accumulated across launches.  wstep windows per launch keeps >= ~64 list entries per warp.
+    long long wstep = 1;
+    {
+        const int win_shift = sjlt_win_shift(d, k);
+        const double per_win = (double)(1LL << win_shift) * (double)k / (double)d / (double)sh.splits;
+        while (wstep < nwin && per_win * (double)wstep < 64.0) wstep *= 2;
+        const char* e = getenv("PLA_SJLT_WINDOWS_PER_LAUNCH");
+        if (e && atoll(e) > 0) wstep = atoll(e);
+    }
+    for (long long w_lo = 0; w_lo < nwin; w_lo += wstep) {
+        const long long w_hi = (w_lo + wstep < nwin) ? w_lo + wstep : nwin;
+        const int acc_flag = (w_lo == 0) ? accumulate : 1;
+#define PLA_SJ_LAUNCH(V, JJ, DD)                                                                                     \
+    sjlt_apply_kernel<V, JJ, DD><<<(unsigned)ctas, 256, 0, st>>>(offsets, entries, d, A, n, lda, bvec, scale, out, ldo, \
+                                                                 out_b, ldob, acc_flag, sh.nchunks, sh.splits, part,  \
+                                                                 nwin, w_lo, w_hi)
+        if (vec2) {
+            if (sh.DPW == 1) PLA_SJ_LAUNCH(2, 4, 1);
+            else if (sh.DPW == 2) PLA_SJ_LAUNCH(2, 2, 2);
+            else PLA_SJ_LAUNCH(2, 1, 4);
+        } else {
+            if (sh.DPW == 1) PLA_SJ_LAUNCH(1, 4, 1);
+            else if (sh.DPW == 2) PLA_SJ_LAUNCH(1, 2, 2);
+            else PLA_SJ_LAUNCH(1, 1, 4);
+        }
+#undef PLA_SJ_LAUNCH
         PLA_LAUNCH_CHECK();
+        if (sh.splits > 1) {
+            long long total = d * (n + 1);
+            int nb = (int)((total + 255) / 256);
+            if (nb > 8 * num_sms()) nb = 8 * num_sms();
+            sjlt_reduce_kernel<<<nb, 256, 0, st>>>(part, sh.splits, d, n, bvec != nullptr ? 1 : 0, scale, out, ldo,
+                                                   out_b, ldob, acc_flag);
+            PLA_LAUNCH_CHECK();
+        }
     }
     return 0;
 }
