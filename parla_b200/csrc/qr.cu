@@ -9,8 +9,11 @@
 // grid barrier per column (the dot products needed by column j+1 are accumulated while column j's
 // reflector is applied).  Trailing matrix: W = V^T C (row-split partials, fixed-order reduction),
 // C -= V (T^T W) with T the compact-WY factor.  Every reduction has a fixed order => deterministic.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/parla_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace pla {
 
@@ -162,6 +165,143 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(const PanelParams 
     }
 }
 
+// ---- Panel factorisation inside ONE thread-block cluster (rows <= cluster_size * QRC_MAXROWS) -----
+// The 16-column panel lives in the shared memory of the cluster's CTAs for the whole factorisation;
+// the per-column partial sums are exchanged through distributed shared memory and ordered by the
+// hardware cluster barrier, so a column step costs ~1 us instead of several L2 round trips.
+constexpr int QRC_THREADS = 512;
+constexpr int QRC_RPT = 3;                               // rows per thread
+constexpr int QRC_MAXROWS = QRC_THREADS * QRC_RPT;       // rows per CTA
+constexpr int QRC_MAXCS = 16;
+constexpr int QRC_XW = QR_NP + QR_NB;                    // exchange record: 17 partial sums + diagonal-row snapshot
+
+__global__ void __launch_bounds__(QRC_THREADS, 1) qr_panel_cluster_kernel(const PanelParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+    extern __shared__ double qc_smem[];
+    double* P = qc_smem;                                           // [QR_NB][QRC_MAXROWS] column-major panel slice
+    double* xch = P + QR_NB * QRC_MAXROWS;                         // [2][QRC_MAXCS][QRC_XW]
+    double* wsum = xch + 2 * QRC_MAXCS * QRC_XW;                   // [16 warps][QR_NP]
+    double* red = wsum + (QRC_THREADS / 32) * QR_NP;               // [QR_NP] cluster-wide totals of the step
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int jb = p.jb;
+    const long long r_begin = p.j0 + (long long)rank * p.rows_per_cta;
+    long long r_end = r_begin + p.rows_per_cta;
+    if (r_end > p.M) r_end = p.M;
+    const int nloc = (int)max(0LL, r_end - r_begin);
+    double* Ap = p.A + p.j0;
+
+    // load my rows (coalesced over the 16 columns of a row: consecutive threads take consecutive elements)
+    for (int idx = tid; idx < nloc * QR_NB; idx += QRC_THREADS) {
+        const int r = idx / QR_NB, c = idx % QR_NB;
+        P[c * QRC_MAXROWS + r] = (c < jb) ? Ap[(r_begin + r) * p.lda + c] : 0.0;
+    }
+    __syncthreads();
+
+    double part[QR_NP];
+#pragma unroll
+    for (int c = 0; c < QR_NP; ++c) part[c] = 0.0;
+    for (int r = tid; r < nloc; r += QRC_THREADS) {
+        if (r_begin + r > p.j0) {
+            const double x = P[r];
+            part[0] = fma(x, x, part[0]);
+#pragma unroll
+            for (int c = 1; c < QR_NB; ++c) part[1 + c] = fma(x, P[c * QRC_MAXROWS + r], part[1 + c]);
+        }
+    }
+
+    for (int j = 0; j < jb; ++j) {
+        const long long dj = p.j0 + j;
+        // ---- CTA-level sums
+#pragma unroll
+        for (int c = 0; c < QR_NP; ++c) {
+            const double v = warp_sum(part[c]);
+            if (lane == 0) wsum[wid * QR_NP + c] = v;
+        }
+        __syncthreads();
+        // ---- publish to every CTA of the cluster (DSMEM): thread (dst, c) writes one double
+        double* rec = xch + ((size_t)(j & 1) * QRC_MAXCS + rank) * QRC_XW;
+        for (int idx = tid; idx < CS * QRC_XW; idx += QRC_THREADS) {
+            const int dst = idx / QRC_XW, c = idx % QRC_XW;
+            double v;
+            if (c < QR_NP) {
+                v = 0.0;
+#pragma unroll
+                for (int q = 0; q < QRC_THREADS / 32; ++q) v += wsum[q * QR_NP + c];
+            } else {
+                // snapshot of the diagonal row (owned by rank 0, local row j), taken before anyone rewrites it
+                v = (rank == 0) ? P[(c - QR_NP) * QRC_MAXROWS + j] : 0.0;
+            }
+            double* remote = cluster.map_shared_rank(rec, dst);
+            remote[c] = v;
+        }
+        cluster.sync();
+        // ---- every CTA reduces the CS records in rank order (identical results everywhere); one warp
+        //      does the sums (lane <-> quantity), the rest of the CTA reads the 17 totals
+        const double* recs = xch + (size_t)(j & 1) * QRC_MAXCS * QRC_XW;
+        if (wid == 0 && lane < QR_NP) {
+            double acc = 0.0;
+            for (int b = 0; b < CS; ++b) acc += recs[b * QRC_XW + lane];
+            red[lane] = acc;
+        }
+        __syncthreads();
+        const double sigma = red[0];
+        const double alpha = recs[QR_NP + j];                       // rank 0's record holds the diagonal row
+        double beta = alpha, tau = 0.0, scale = 0.0;
+        if (sigma != 0.0) {
+            const double nrm = sqrt(fma(alpha, alpha, sigma));
+            beta = alpha >= 0.0 ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        double wv[QR_NB];
+#pragma unroll
+        for (int c = 0; c < QR_NB; ++c) {
+            wv[c] = 0.0;
+            if (c > j && c < jb) wv[c] = tau * fma(scale, red[1 + c], recs[QR_NP + c]);
+        }
+        if (rank == 0 && tid == 0) p.tau[j] = tau;
+        // ---- apply to my rows (shared memory), gathering the dots of column j + 1
+#pragma unroll
+        for (int c = 0; c < QR_NP; ++c) part[c] = 0.0;
+        for (int r = tid; r < nloc; r += QRC_THREADS) {
+            const long long i = r_begin + r;
+            if (i < dj) continue;
+            if (i == dj) {
+                P[j * QRC_MAXROWS + r] = beta;
+#pragma unroll
+                for (int c = 0; c < QR_NB; ++c)
+                    if (c > j && c < jb) P[c * QRC_MAXROWS + r] -= wv[c];
+            } else {
+                const double v = P[j * QRC_MAXROWS + r] * scale;
+                P[j * QRC_MAXROWS + r] = v;
+                double a[QR_NB];
+#pragma unroll
+                for (int c = 0; c < QR_NB; ++c) {
+                    a[c] = 0.0;
+                    if (c > j && c < jb) { a[c] = fma(-v, wv[c], P[c * QRC_MAXROWS + r]); P[c * QRC_MAXROWS + r] = a[c]; }
+                }
+                if (i > dj + 1 && j + 1 < jb) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int c = 0; c < QR_NB; ++c) if (c == j + 1) x = a[c];
+                    part[0] = fma(x, x, part[0]);
+#pragma unroll
+                    for (int c = 0; c < QR_NB; ++c)
+                        if (c > j + 1 && c < jb) part[1 + c] = fma(x, a[c], part[1 + c]);
+                }
+            }
+        }
+        __syncthreads();          // row dj+1 (next diagonal) is final before rank 0 snapshots it
+    }
+    // ---- write the factored panel back
+    for (int idx = tid; idx < nloc * QR_NB; idx += QRC_THREADS) {
+        const int r = idx / QR_NB, c = idx % QR_NB;
+        if (c < jb) Ap[(r_begin + r) * p.lda + c] = P[c * QRC_MAXROWS + r];
+    }
+    cluster.sync();               // no CTA may exit while others can still write into its shared memory
+}
+
 // ---- Gram of the panel's reflectors: Gpart[cta][16][16] = sum_rows V[i][a] V[i][b]
 struct VView {
     const double* A; long long lda; long long j0; int jb;
@@ -289,10 +429,20 @@ __global__ void __launch_bounds__(QR_THREADS) qr_trail_reduce_kernel(const Trail
 #pragma unroll
     for (int k = 0; k < QR_NB; ++k) acc[k] = 0.0;
     if (c < p.nc) {
-        for (int sp = grp; sp < p.splits; sp += 8) {
-            const double* src = p.wpart + (size_t)sp * QR_NB * p.nc + c;
+        // four independent batches of loads in flight per thread (fixed association order)
+        for (int sp = grp; sp < p.splits; sp += 32) {
+            double t4[4][QR_NB];
 #pragma unroll
-            for (int k = 0; k < QR_NB; ++k) acc[k] += src[(size_t)k * p.nc];
+            for (int u = 0; u < 4; ++u) {
+                const int s2 = sp + 8 * u;
+                const double* src = p.wpart + (size_t)(s2 < p.splits ? s2 : 0) * QR_NB * p.nc + c;
+#pragma unroll
+                for (int k = 0; k < QR_NB; ++k) t4[u][k] = (s2 < p.splits) ? src[(size_t)k * p.nc] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < QR_NB; ++k) acc[k] += t4[u][k];
         }
     }
 #pragma unroll
@@ -478,10 +628,34 @@ static int run_panel(double* A, long long lda, long long M, long long j0, int jb
     PanelParams pp;
     pp.A = A; pp.lda = lda; pp.M = M; pp.j0 = j0; pp.jb = jb; pp.tau = tau + j0; pp.gpart = w.gpart;
     pp.drowbuf = w.drowbuf; pp.counter = w.counter; pp.rows_per_cta = (rows + G - 1) / G;
-    PLA_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st));
-    void* args[] = {(void*)&pp};
-    PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
-    note_launch();
+    bool launched = false;
+    static const bool use_cluster = [] { const char* e = getenv("PLA_QR_CLUSTER"); return !(e && e[0] == '0'); }();
+    if (use_cluster && rows >= 64 && rows <= (long long)QRC_MAXCS * QRC_MAXROWS) {
+        // smallest cluster (1, 2, 4, 8, 16 CTAs) whose shared memory holds the panel
+        int cs = 1;
+        while ((long long)cs * QRC_MAXROWS < rows) cs *= 2;
+        pp.rows_per_cta = (rows + cs - 1) / cs;
+        const size_t smem = (size_t)(QR_NB * QRC_MAXROWS + 2 * QRC_MAXCS * QRC_XW + (QRC_THREADS / 32) * QR_NP + QR_NP + 7) * 8;
+        PLA_CUDA(cudaFuncSetAttribute(qr_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (cs > 8)
+            PLA_CUDA(cudaFuncSetAttribute(qr_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs); cfg.blockDim = dim3(QRC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        launched = (cudaLaunchKernelEx(&cfg, qr_panel_cluster_kernel, pp) == cudaSuccess);
+        if (launched) note_launch();
+        else (void)cudaGetLastError();      // cluster not schedulable on this part: use the grid-barrier kernel
+    }
+    if (!launched) {
+        pp.rows_per_cta = (rows + G - 1) / G;
+        PLA_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(unsigned int), st));
+        void* args[] = {(void*)&pp};
+        PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_panel_kernel, dim3(G), dim3(QR_THREADS), args, 0, st));
+        note_launch();
+    }
     // compact-WY factor T
     int GG = (int)((rows + 4 * QR_TR - 1) / (4 * QR_TR));
     if (GG > sms) GG = sms;
