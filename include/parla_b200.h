@@ -106,6 +106,24 @@ int pla_lsqr_init_f64(int64_t n, const double* t, const double* zss, const doubl
                       double* w, double* dstate, int* istate, void* stream);
 int pla_lsqr_step_f64(int64_t n, const double* t, const double* zss, double* x, double* v, double* w,
                       double* dstate, int* istate, double* arnorm_hist, void* stream);
+/* LSQR on the adjoint operator A_pc^T (under-determined branch of PcSS2, saddle.py:203-214; SPU1,
+ * least_squares.py:425-494): short vector u (length r), long vectors v~, w, x (length of A's rows).
+ *   init  : u = c_pc / |c_pc|
+ *   init2 : after the first pass (v~ = A_pc u): alfa = |v~|
+ *   head  : u <- normalised (t / alfa - alfa u), t = M^T A^T v~;  sets (sa, su) of the next pass
+ *   tail  : alfa = |v~| from zss[nz], rotations, stopping tests, arnorm history
+ *   long  : x += t1 w ; w <- v~/alfa + t2 w ; |w|^2 -> state (call once per long block: top rows, ridge rows)
+ * `itn` is the iteration the long update belongs to (0 = initialisation); it is skipped on the device
+ * when LSQR had already stopped before that iteration.                                            */
+int pla_lsqr_under_init_f64(int64_t r, const double* cpc, double* u, double atol, double btol, double conlim,
+                            int iter_lim, double* dstate, int* istate, void* stream);
+int pla_lsqr_under_init2_f64(int64_t nz, const double* zss, double* dstate, int* istate, void* stream);
+int pla_lsqr_under_head_f64(int64_t r, const double* t, double* u, double* dstate, const int* istate, void* stream);
+int pla_lsqr_under_tail_f64(int64_t nz, const double* zss, double* dstate, int* istate, double* arnorm_hist,
+                            void* stream);
+int pla_lsqr_under_long_f64(int64_t len, const double* vt, double* x, double* w, double* dstate, const int* istate,
+                            int itn, int add_to_ww, void* ws, size_t ws_bytes, void* stream);
+
 /* ridge (delta > 0) rows of [A; sqrt(delta) I], applied implicitly (the reference materialises
  * them: parla/comps/preconditioning.py:6-13,35-36):
  *   ub <- sa * sd * xw + su * ub ;  zss[0..n) += sd * ub ;  zss[n] += |ub|^2                      */

@@ -20,7 +20,7 @@ import scipy.linalg as sla
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+REF = next((a for a in sys.argv[1:] if not a.startswith("--")), "/root/reference")
 sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
@@ -103,6 +103,27 @@ def spo_case(name, m, n, seed, sketch, mode, delta, sf=4, tol=1e-12, iter_lim=10
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
 
 
+def spu_case(name, m, n, seed, cond=1e3, sf=4, tol=1e-12, iter_lim=100, rng_seed=1):
+    """Under-determined least squares (min |y| s.t. A'y = c), SPU1 (least_squares.py:425-494)."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((m, n)) * np.logspace(0, np.log10(cond), n)
+    c = rng.standard_normal(n)
+    ref_gen, orc_gen = Tape(rsko.SkOpSJ(8)), Tape(orc.SkOpSJ(8))
+    y_ref, log_ref = rla.SPU1(ref_gen, sf)(A, c, tol, iter_lim, np.random.default_rng(rng_seed), logging=True)
+    y_orc, log_orc = orc.SPU1(orc_gen, sf)(A, c, tol, iter_lim, np.random.default_rng(rng_seed), logging=True)
+    assert (ref_gen.ops[0] != orc_gen.ops[0]).nnz == 0
+    rows, signs, k = orc.sjlt_index_form(ref_gen.ops[0])
+    e_y = relerr(y_orc, y_ref)
+    its = (log_ref.errors.size - 1, log_orc.errors.size - 1)
+    print(f"{name:28s} iters ref/orc {its}  |dy|/|y| {e_y:.2e}  constraint |A'y-c|/|c| "
+          f"{np.linalg.norm(A.T @ y_ref - c) / np.linalg.norm(c):.2e}")
+    assert e_y < 1e-9 and abs(its[0] - its[1]) <= 1, (e_y, its)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), m=m, n=n, seed=seed, cond=cond, sf=sf, tol=tol,
+                        iter_lim=iter_lim, rng_seed=rng_seed, y_norm=np.linalg.norm(y_ref),
+                        y_probe=y_ref[::max(1, m // 64)], errors=log_ref.errors, A_sha=digest(A), c_sha=digest(c),
+                        S_rows=rows.astype(np.int16), S_signs=signs, vec_nnz=k)
+
+
 def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pass=2, evd=False):
     rng = np.random.default_rng(seed)
     if evd:
@@ -168,6 +189,10 @@ def philox_case():
 
 
 if __name__ == "__main__":
+    if "--only-spu" in sys.argv:
+        spu_case("spu1_sjlt_800x50", 800, 50, 31)
+        spu_case("spu1_sjlt_2000x96", 2000, 96, 32, cond=1e5)
+        sys.exit(0)
     philox_case()
     # sketch-and-precondition least squares: {SJLT, Gaussian} x {qr, svd, chol} x {delta}
     spo_case("spo_sjlt_qr_600x40", 600, 40, 11, 'sjlt', 'qr', 0.0)
@@ -186,4 +211,6 @@ if __name__ == "__main__":
     lowrank_case("svd1_qb2_tol_200x50", 200, 50, 45, 50, 23, blk=5, tol=1e-3)
     lowrank_case("svd1_qb1_over_50x200", 50, 200, 15, 10, 24, over=5)
     lowrank_case("evd1_qb1_120", 120, 120, 12, 12, 25, evd=True)
+    spu_case("spu1_sjlt_800x50", 800, 50, 31)
+    spu_case("spu1_sjlt_2000x96", 2000, 96, 32, cond=1e5)
     print("golden fixtures written to", OUT)

@@ -339,6 +339,65 @@ def pcss2_overdetermined(A, b, delta, tol, iter_lim, R, upper_tri, z0):
     return x, y, res.arnorms
 
 
+class _Transposed:
+    """The adjoint view `A_pc.T` that saddle.py:206 hands to lsqr."""
+
+    def __init__(self, op):
+        self.op = op
+        self.shape = (op.shape[1], op.shape[0])
+
+    def matvec(self, y):
+        return self.op.rmatvec(y)
+
+    def rmatvec(self, z):
+        return self.op.matvec(z)
+
+
+def pcss2_underdetermined(A, c, delta, tol, iter_lim, R, upper_tri):
+    """Under-determined branch of PcSS2.__call__, saddle.py:203-214.  Returns (x, y, arnorms):
+    y is the minimum-norm solution of (A M)' y = M' c; x = (A'y - c)/delta when delta > 0, else NaN."""
+    m, n = A.shape
+    op = LiftedPrecondOperator(A, delta, R, upper_tri)
+    c_pc = op.precond_t(c)
+    res = lsqr(_Transposed(op), c_pc, atol=tol, btol=tol, iter_lim=iter_lim)
+    y = res.x
+    if delta > 0:
+        y = y[:m]
+        x = (A.T @ y - c) / delta
+    else:
+        x = np.nan * np.empty(n)
+    return x, y, res.arnorms
+
+
+class SPU1:
+    """SVD-based sketch-and-precondition for under-determined least squares
+    (min ||y|| s.t. A'y = c), least_squares.py:425-494."""
+
+    def __init__(self, sketch_op_gen, sampling_factor):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+
+    def __call__(self, A, c, tol, iter_lim, rng, logging=True):
+        m, n = A.shape
+        d = dim_checks(self.sampling_factor, m, n)
+        rng = np.random.default_rng(rng)
+        clock = time.time if logging else (lambda: 0.0)
+        log = SketchAndPrecondLog()
+        t = clock()
+        S = self.sketch_op_gen(d, m, rng)                       # :469-471
+        A_ske = S @ A
+        log.time_sketch = clock() - t
+        t = clock()
+        M, _U, _s, _Vh = svd_right_precond(A_ske)               # :475
+        log.time_factor = clock() - t
+        t = clock()
+        x, y, arnorms = pcss2_underdetermined(A, c, 0.0, tol, iter_lim, M, False)    # :480
+        log.time_iterate = clock() - t
+        if logging:
+            log.wrap_up(arnorms, float(np.linalg.norm(A @ (M @ (M.T @ c)))))        # :486
+        return y, log
+
+
 def dim_checks(sampling_factor, n_rows, n_cols):
     """least_squares.py:89-104."""
     assert n_rows >= n_cols

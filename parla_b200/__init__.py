@@ -12,7 +12,7 @@ from .comps.qb import QB1, QB2, QBDecomposer
 from .comps.rangefinders import RF1, RangeFinder
 from .comps.determiter.logging import SketchAndPrecondLog
 from .comps.determiter.saddle import PcSS2, PrecondSaddleSolver
-from .drivers.least_squares import SPO, SSO1, OverLstsqSolver
+from .drivers.least_squares import SPO, SSO1, OverLstsqSolver, SPU1, UnderLstsqSolver
 from .drivers.svd import SVD1, SVDecomposer
 from .drivers.evd import EVD1, EVDecomposer
 from .parallel import RowSharded

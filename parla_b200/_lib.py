@@ -28,6 +28,11 @@ SIGNATURES = {
                                   c_vp, c_vp, c_vp]),
     "pla_lsqr_step_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pla_lsqr_ridge_f64": (c_int, [c_i64, c_dbl, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
+    "pla_lsqr_under_init_f64": (c_int, [c_i64, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp]),
+    "pla_lsqr_under_init2_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "pla_lsqr_under_head_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pla_lsqr_under_tail_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pla_lsqr_under_long_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_sz, c_vp]),
     "pla_sjlt_plan_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pla_sjlt_plan_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pla_sjlt_plan_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),

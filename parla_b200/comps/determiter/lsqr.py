@@ -84,3 +84,77 @@ def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=F
         return x, 0, 0, ds[14], ds[14], 0.0, 0.0, np.float64(ds[11]), 0.0, var
     arn = hist[:itn].cpu().numpy()
     return x, istop, itn, ds[14], ds[14], ds[4], ds[13], arn, ds[12], var
+
+
+LSU_WW = 23      # dstate slot holding |w|^2 (see csrc/lsqr_step.cu)
+
+
+def lsqr_adjoint(A, c_pc, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None):
+    """LSQR applied to ``A.T`` for a PrecondOperator ``A`` (what saddle.py:206 does with ``A_pc.T``):
+    minimum-norm y with (A_pc)^T y = c_pc.  The long vectors (v~, w, y) live on the rows of A (and on
+    the n ridge rows when delta > 0); the same fused pass as the over-determined case does
+    v~ <- A M u - (beta/alfa) v~ and z = A^T v~ in one read of A.
+    Returns (y_top, y_ridge_or_None, istop, itn, arnorms, dstate)."""
+    r = A.shape[1]
+    dev = c_pc.device
+    if iter_lim is None:
+        iter_lim = 2 * A.shape[0]
+    iter_lim = int(iter_lim)
+    nA, m_loc = A.n, A.m_local
+    ridge = A.delta > 0
+    u = torch.empty(r, dtype=F64, device=dev)
+    t = torch.empty(r, dtype=F64, device=dev)
+    xw = torch.empty(nA, dtype=F64, device=dev)
+    vt = torch.zeros(m_loc, dtype=F64, device=dev)
+    y = torch.zeros(m_loc, dtype=F64, device=dev)
+    w = torch.zeros(m_loc, dtype=F64, device=dev)
+    vb = torch.zeros(nA, dtype=F64, device=dev) if ridge else None
+    yb = torch.zeros(nA, dtype=F64, device=dev) if ridge else None
+    wb = torch.zeros(nA, dtype=F64, device=dev) if ridge else None
+    zss = torch.empty(nA + 1, dtype=F64, device=dev)
+    dstate = torch.zeros(K.LSQR_NDOUBLE, dtype=F64, device=dev)
+    istate = torch.zeros(K.LSQR_NINT, dtype=torch.int32, device=dev)
+    hist = torch.full((iter_lim,), -1.0, dtype=F64, device=dev)
+    sc = dstate[K.LSQR_SA:K.LSQR_SA + 2]
+    istop_dev = istate[0:1]
+
+    def long_update(itn):
+        K.lsqr_under_long(vt, y, w, dstate, istate, itn)
+        if A.group is not None:                           # |w|^2 over all row shards
+            from ...parallel import allreduce_
+            allreduce_(dstate[LSU_WW:LSU_WW + 1], A.group)
+        if ridge:
+            K.lsqr_under_long(vb, yb, wb, dstate, istate, itn, add_to_ww=True)
+
+    K.lsqr_under_init(c_pc, u, atol, btol, conlim, iter_lim, dstate, istate)
+    A.bidiag_pass(u, vt, vb, zss, xw, t, sc=sc)           # v~_0 = A_pc u_0 (su = 0), t = M^T A^T v~_0
+    K.lsqr_under_init2(nA, zss, dstate, istate)
+    long_update(0)
+
+    pinned = [torch.zeros(K.LSQR_NINT, dtype=torch.int32).pin_memory() for _ in range(POLL_LAG + 1)]
+    events = [torch.cuda.Event() for _ in range(POLL_LAG + 1)]
+
+    def post(slot):
+        pinned[slot].copy_(istate, non_blocking=True)
+        events[slot].record()
+
+    post(0)
+    events[0].synchronize()
+    if int(pinned[0][0]) == 0:
+        for it in range(iter_lim):
+            if it >= POLL_LAG:
+                slot = (it - POLL_LAG) % (POLL_LAG + 1)
+                events[slot].synchronize()
+                if int(pinned[slot][0]) != 0:
+                    break
+            K.lsqr_under_head(t, u, dstate, istate)
+            A.bidiag_pass(u, vt, vb, zss, xw, t, sc=sc, istop=istop_dev)
+            K.lsqr_under_tail(nA, zss, dstate, istate, hist)
+            long_update(it + 1)
+            post(it % (POLL_LAG + 1))
+    torch.cuda.current_stream().synchronize()
+    ist = istate.cpu().numpy()
+    istop, itn = int(ist[0]), int(ist[1])
+    if istop == 100:
+        return y, yb, 0, 0, np.float64(float(dstate[11])), dstate
+    return y, yb, istop, itn, hist[:itn].cpu().numpy(), dstate

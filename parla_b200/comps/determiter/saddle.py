@@ -6,7 +6,7 @@ under-determined branch (:203-214) is a "next" row of SURVEY.md 8(f).
 """
 import torch
 
-from .lsqr import lsqr
+from .lsqr import lsqr, lsqr_adjoint
 from ..preconditioning import a_lift_precond
 
 
@@ -40,7 +40,15 @@ class PcSS2(PrecondSaddleSolver):
             y = A_pc.residual_and_atb(x, b_loc) if _need_y else None
             return x, y, result[7]
         if b is None or float(torch.linalg.vector_norm(getattr(b, "local", b))) == 0:
-            raise NotImplementedError("under-determined branch (saddle.py:203-214) is not on the hot path yet")
+            # Under-determined least squares (saddle.py:203-214): LSQR on A_pc^T with rhs M^T c
+            c_pc = A_pc.precond_t(c)
+            y, _y_ridge, _istop, _itn, arnorms, _ = lsqr_adjoint(A_pc, c_pc, atol=tol, btol=tol, iter_lim=iter_lim)
+            n = A_pc.n
+            if delta > 0:
+                x = (A_pc.rmatvec_plain(y) - c) / delta
+            else:
+                x = torch.full((n,), float("nan"), dtype=y.dtype, device=y.device)
+            return x, y, arnorms
         raise ValueError('One of "b" or "c" must be zero.')
 
     exec = __call__

@@ -78,6 +78,20 @@ class PrecondOperator:
         self.precond_t(zss[:self.n], out=t)
         return t
 
+    def rmatvec_plain(self, y):
+        """A^T y (no preconditioner, no ridge rows), summed over row shards."""
+        zss = K.stream_pass(self.A, u=y, flags=K.PASS_AXPY)
+        self.passes += 1
+        allreduce_(zss, self.group)
+        return zss[:self.n].clone()
+
+    def matvec_plain(self, x):
+        """A x on this rank's rows."""
+        y = torch.zeros(self.m_local, dtype=F64, device=x.device)
+        K.stream_pass(self.A, w=x, u=y, sa=1.0, su=0.0, flags=K.PASS_DOT)
+        self.passes += 1
+        return y
+
     def residual_and_atb(self, x, b):
         """y = b - A x and A^T b in one pass (saddle.py:199 and least_squares.py:361 fused)."""
         y = b.clone()

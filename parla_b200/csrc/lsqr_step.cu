@@ -202,9 +202,207 @@ __global__ void __launch_bounds__(LS_THREADS) lsqr_ridge_kernel(long long n, dou
     if (threadIdx.x == 0) zss[n] += acc;
 }
 
+// ------------------------------------------------------------------------------------------------
+// LSQR on the ADJOINT operator B = A_pc^T (under-determined problems, saddle.py:203-214): the short
+// vector is u (rank of the preconditioner), the long ones are v, w, x (rows of A).  With the
+// unnormalised v~ kept by the streaming pass (v = v~ / alfa):
+//   head : u <- (t / alfa - alfa u) normalised, beta = its norm        (lsqr.py:421-425 with roles swapped)
+//   pass : v~ <- A (M u) - (beta / alfa) v~ ,  z = A^T v~ ,  |v~|^2     (lsqr.py:427-430)
+//   tail : alfa = |v~|, plane rotations, stopping tests                (:434-526)
+//   long : x += t1 w ;  w <- v~ / alfa + t2 w ;  |w|^2                  (:449-457)
+constexpr int LSU_T1 = 20, LSU_T2 = 21, LSU_INVA = 22, LSU_WW = 23;
+constexpr int LSU_LONG_ITN = 3;          // istate: iteration whose long-vector update is due
+
+__global__ void __launch_bounds__(LS_THREADS) lsqr_under_init_kernel(long long r, const double* __restrict__ cpc,
+                                                                     double* u, double atol, double btol, double ctol,
+                                                                     int iter_lim, double* ds, int* is) {
+    __shared__ double scratch[33];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < r; i += blockDim.x) acc = fma(cpc[i], cpc[i], acc);
+    const double beta = sqrt(block_sum(acc, scratch));
+    for (long long i = threadIdx.x; i < r; i += blockDim.x) u[i] = beta > 0.0 ? cpc[i] / beta : cpc[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < PLA_LSQR_NDOUBLE; ++i) ds[i] = 0.0;
+        ds[PLA_LSQR_BETA] = beta;
+        ds[PLA_LSQR_PHIBAR] = beta;
+        ds[PLA_LSQR_BNORM] = beta;
+        ds[PLA_LSQR_RNORM] = beta;
+        ds[PLA_LSQR_CS2] = -1.0;
+        ds[PLA_LSQR_SA] = 1.0;
+        ds[PLA_LSQR_SU] = 0.0;
+        ds[PLA_LSQR_ATOL] = atol; ds[PLA_LSQR_BTOL] = btol; ds[PLA_LSQR_CTOL] = ctol;
+        for (int i = 0; i < PLA_LSQR_NINT; ++i) is[i] = 0;
+        is[PLA_LSQR_ITERLIM] = iter_lim;
+    }
+}
+
+// after the first pass (v~_0 = A_pc u_0): alfa_0 = |v~_0|, w = v = v~_0 / alfa_0 (done by the long kernel, t1 = t2 = 0)
+__global__ void lsqr_under_init2_kernel(long long nz, const double* __restrict__ zss, double* ds, int* is) {
+    const double beta = ds[PLA_LSQR_BETA];
+    const double alfa = beta > 0.0 ? sqrt(zss[nz]) : 0.0;
+    ds[PLA_LSQR_ALFA] = alfa;
+    ds[PLA_LSQR_RHOBAR] = alfa;
+    ds[PLA_LSQR_ARNORM] = alfa * beta;
+    ds[LSU_T1] = 0.0; ds[LSU_T2] = 0.0;
+    ds[LSU_INVA] = alfa > 0.0 ? 1.0 / alfa : 0.0;
+    ds[LSU_WW] = alfa > 0.0 ? 1.0 : 0.0;
+    is[LSU_LONG_ITN] = 0;
+    is[PLA_LSQR_ISTOP] = (alfa * beta == 0.0) ? 100 : 0;
+}
+
+__global__ void __launch_bounds__(LS_THREADS) lsqr_under_head_kernel(long long r, const double* __restrict__ t, double* u,
+                                                                     double* ds, const int* is) {
+    if (is[PLA_LSQR_ISTOP] != 0) return;
+    __shared__ double scratch[33];
+    const double alfa = ds[PLA_LSQR_ALFA], anorm = ds[PLA_LSQR_ANORM];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < r; i += blockDim.x) {
+        const double ui = t[i] / alfa - alfa * u[i];
+        u[i] = ui;
+        acc = fma(ui, ui, acc);
+    }
+    const double beta = sqrt(block_sum(acc, scratch));
+    if (beta > 0.0)
+        for (long long i = threadIdx.x; i < r; i += blockDim.x) u[i] = u[i] / beta;
+    if (threadIdx.x == 0) {
+        ds[PLA_LSQR_BETA] = beta;
+        if (beta > 0.0) ds[PLA_LSQR_ANORM] = sqrt(anorm * anorm + alfa * alfa + beta * beta);
+        ds[PLA_LSQR_SA] = beta > 0.0 ? 1.0 : 0.0;           // beta == 0: v~ is left as it is (lsqr.py:424)
+        ds[PLA_LSQR_SU] = beta > 0.0 ? -beta / alfa : 1.0;
+    }
+}
+
+__global__ void lsqr_under_tail_kernel(long long nz, const double* __restrict__ zss, double* ds, int* is, double* hist) {
+    if (is[PLA_LSQR_ISTOP] != 0) return;
+    const double eps = 2.220446049250313e-16;
+    const double beta = ds[PLA_LSQR_BETA];
+    double alfa = ds[PLA_LSQR_ALFA];
+    const double alfa_old = alfa;
+    if (beta > 0.0) alfa = sqrt(zss[nz]);
+    double cs, sn, rho;
+    sym_ortho(ds[PLA_LSQR_RHOBAR], beta, cs, sn, rho);
+    const double theta = sn * alfa;
+    const double rhobar = -cs * alfa;
+    const double phi = cs * ds[PLA_LSQR_PHIBAR];
+    const double phibar = sn * ds[PLA_LSQR_PHIBAR];
+    const double tau = sn * phi;
+    const double ddnorm = ds[PLA_LSQR_DDNORM] + ds[LSU_WW] / (rho * rho);
+    const double cs2 = ds[PLA_LSQR_CS2], sn2 = ds[PLA_LSQR_SN2], zprev = ds[PLA_LSQR_Z];
+    double xxnorm = ds[PLA_LSQR_XXNORM];
+    const double delta = sn2 * rho, gambar = -cs2 * rho, rhs = phi - delta * zprev;
+    const double zbar = rhs / gambar;
+    const double xnorm = sqrt(xxnorm + zbar * zbar);
+    const double gamma = sqrt(gambar * gambar + theta * theta);
+    const double z = rhs / gamma;
+    xxnorm += z * z;
+    const double anorm = ds[PLA_LSQR_ANORM];
+    const double acond = anorm * sqrt(ddnorm);
+    const double rnorm = sqrt(phibar * phibar);
+    const double arnorm = alfa * fabs(tau);
+    const double bnorm = ds[PLA_LSQR_BNORM];
+    const double atol = ds[PLA_LSQR_ATOL], btol = ds[PLA_LSQR_BTOL], ctol = ds[PLA_LSQR_CTOL];
+    const double test1 = rnorm / bnorm, test2 = arnorm / (anorm * rnorm + eps), test3 = 1.0 / (acond + eps);
+    const double tt1 = test1 / (1.0 + anorm * xnorm / bnorm), rtol = btol + atol * anorm * xnorm / bnorm;
+    const int itn_prev = is[PLA_LSQR_ITN];
+    hist[itn_prev] = ds[PLA_LSQR_ARNORM];
+    const int itn = itn_prev + 1;
+    int istop = 0;
+    if (itn >= is[PLA_LSQR_ITERLIM]) istop = 7;
+    if (1.0 + test3 <= 1.0) istop = 6;
+    if (1.0 + test2 <= 1.0) istop = 5;
+    if (1.0 + tt1 <= 1.0) istop = 4;
+    if (test3 <= ctol) istop = 3;
+    if (test2 <= atol) istop = 2;
+    if (test1 <= rtol) istop = 1;
+    ds[PLA_LSQR_ALFA] = alfa; ds[PLA_LSQR_RHOBAR] = rhobar; ds[PLA_LSQR_PHIBAR] = phibar;
+    ds[PLA_LSQR_DDNORM] = ddnorm; ds[PLA_LSQR_XXNORM] = xxnorm; ds[PLA_LSQR_Z] = z;
+    ds[PLA_LSQR_CS2] = gambar / gamma; ds[PLA_LSQR_SN2] = theta / gamma;
+    ds[PLA_LSQR_ARNORM] = arnorm; ds[PLA_LSQR_XNORM] = xnorm; ds[PLA_LSQR_ACOND] = acond; ds[PLA_LSQR_RNORM] = rnorm;
+    ds[LSU_T1] = phi / rho;
+    ds[LSU_T2] = -theta / rho;
+    // w <- v + t2 w with v = v~/alfa when the step produced a new v~ (beta > 0, alfa > 0); otherwise v is unchanged,
+    // i.e. v~ / alfa_old
+    ds[LSU_INVA] = (beta > 0.0 && alfa > 0.0) ? 1.0 / alfa : (alfa_old > 0.0 ? 1.0 / alfa_old : 0.0);
+    is[PLA_LSQR_ITN] = itn;
+    is[LSU_LONG_ITN] = itn;
+    is[PLA_LSQR_ISTOP] = istop;
+}
+
+// x += t1 w ; w <- v~ * inva + t2 w ; part[block] = sum w_new^2.   Runs iff istate says iteration `itn` is due.
+__global__ void __launch_bounds__(256) lsqr_under_long_kernel(long long len, const double* __restrict__ vt, double* x,
+                                                              double* w, const double* ds, const int* is, int itn,
+                                                              double* part) {
+    __shared__ double scratch[33];
+    if (is[LSU_LONG_ITN] != itn || (itn > 0 && is[PLA_LSQR_ITN] != itn)) { if (threadIdx.x == 0) part[blockIdx.x] = -1.0; return; }
+    const double t1 = ds[LSU_T1], t2 = ds[LSU_T2], inva = ds[LSU_INVA];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+        x[i] = fma(t1, wi, x[i]);
+        const double wn = fma(vt[i], inva, t2 * wi);
+        w[i] = wn;
+        acc = fma(wn, wn, acc);
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+// ww_out[0] (+)= sum of the partials of one long-vector update (skipped launches wrote -1)
+__global__ void __launch_bounds__(256) lsqr_under_long_reduce_kernel(const double* part, int nb, int add, double* ww_out) {
+    __shared__ double scratch[33];
+    if (part[0] < 0.0) return;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += part[i];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) ww_out[0] = add ? ww_out[0] + acc : acc;
+}
+
 }  // namespace pla
 
 using namespace pla;
+
+extern "C" int pla_lsqr_under_init_f64(int64_t r, const double* cpc, double* u, double atol, double btol, double conlim,
+                                       int iter_lim, double* dstate, int* istate, void* stream) {
+    PLA_CHECK_ARG(r >= 1, 1, "r < 1");
+    PLA_CHECK_ARG(cpc && u && dstate && istate, 2, "null argument");
+    PLA_CHECK_ARG(iter_lim >= 1, 7, "iter_lim < 1");
+    lsqr_under_init_kernel<<<1, LS_THREADS, 0, (cudaStream_t)stream>>>(r, cpc, u, atol, btol, conlim > 0 ? 1.0 / conlim : 0.0,
+                                                                        iter_lim, dstate, istate);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int pla_lsqr_under_init2_f64(int64_t nz, const double* zss, double* dstate, int* istate, void* stream) {
+    PLA_CHECK_ARG(zss && dstate && istate, 2, "null argument");
+    lsqr_under_init2_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(nz, zss, dstate, istate);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int pla_lsqr_under_head_f64(int64_t r, const double* t, double* u, double* dstate, const int* istate,
+                                       void* stream) {
+    PLA_CHECK_ARG(r >= 1 && t && u && dstate && istate, 1, "bad argument");
+    lsqr_under_head_kernel<<<1, LS_THREADS, 0, (cudaStream_t)stream>>>(r, t, u, dstate, istate);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int pla_lsqr_under_tail_f64(int64_t nz, const double* zss, double* dstate, int* istate, double* arnorm_hist,
+                                       void* stream) {
+    PLA_CHECK_ARG(zss && dstate && istate && arnorm_hist, 2, "null argument");
+    lsqr_under_tail_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(nz, zss, dstate, istate, arnorm_hist);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int pla_lsqr_under_long_f64(int64_t len, const double* vt, double* x, double* w, double* dstate,
+                                       const int* istate, int itn, int add_to_ww, void* ws, size_t ws_bytes, void* stream) {
+    PLA_CHECK_ARG(len >= 1 && vt && x && w && dstate && istate, 1, "bad argument");
+    int nb = (int)((len + 255) / 256);
+    if (nb > 4 * num_sms()) nb = 4 * num_sms();
+    PLA_CHECK_ARG(ws != nullptr && ws_bytes >= (size_t)nb * 8, 9, "workspace too small");
+    lsqr_under_long_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(len, vt, x, w, dstate, istate, itn, (double*)ws);
+    PLA_LAUNCH_CHECK();
+    lsqr_under_long_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)ws, nb, add_to_ww, dstate + LSU_WW);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
+
 
 extern "C" int pla_lsqr_init_f64(int64_t n, const double* t, const double* zss, const double* bsq_dev, double atol,
                                  double btol, double conlim, int iter_lim, const double* x0, double* x, double* v,

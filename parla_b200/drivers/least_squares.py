@@ -262,3 +262,68 @@ class SPO(OverLstsqSolver):
         return _to_host(x, host), log
 
     exec = __call__
+
+
+class UnderLstsqSolver:
+    """min ||y|| s.t. A' y = c for a tall A.  Interface of least_squares.py:372-417."""
+
+    def __call__(self, A, c, tol, iter_lim, rng, logging=False):
+        raise NotImplementedError()
+
+    exec = __call__
+
+
+class SPU1(UnderLstsqSolver):
+    """SVD-based sketch-and-precondition for under-determined least squares
+    (least_squares.py:425-494): sketch A, M = V / sigma from the SVD of the sketch, then LSQR on
+    (A M)^T (PcSS2's under-determined branch)."""
+
+    def __init__(self, sketch_op_gen, sampling_factor: int):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+        self.iterative_solver = dsad.PcSS2()  # implements LSQR
+
+    def __call__(self, A, c, tol, iter_lim, rng, logging=True):
+        host = None
+        if isinstance(A, np.ndarray):
+            host = "numpy"
+            dev = torch.device("cuda", torch.cuda.current_device())
+            A = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float64)).to(dev)
+            c = torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)).to(dev)
+        n_rows, n_cols = A.shape
+        d = dim_checks(self.sampling_factor, n_rows, n_cols)
+        rng = np.random.default_rng(rng)
+        A_loc, _, group = unwrap(A)
+
+        quick_time = _clock(logging)
+        log = SketchAndPrecondLog()
+
+        tic = quick_time()                                                    # :467-471
+        _, W = _sketch(self.sketch_op_gen, d, A, None, 0.0, rng)
+        log.time_sketch = quick_time() - tic
+
+        tic = quick_time()                                                    # :474-476
+        M, U, sigma, Vh = rpc.svd_right_precond(W[:, :n_cols])
+        log.time_factor = quick_time() - tic
+
+        tic = quick_time()                                                    # :479-483
+        res = self.iterative_solver(A, None, c, 0.0, tol, iter_lim, M, False, None)
+        log.time_iterate = quick_time() - tic
+        y_star = res[1]
+
+        if logging:                                                           # :485-492
+            op = self.iterative_solver.last_op
+            Av = op.matvec_plain(op.precond(op.precond_t(c)))
+            nrm = math.sqrt(float(allreduce_(K.sumsq(Av), group)))
+            log.wrap_up(res[2], nrm)
+            log.iters = int(np.atleast_1d(res[2]).size)
+            log.passes_over_A = op.passes + 1
+            log.error_desc = """
+            The logs produced by this algorithm measure error as\n
+                || (A M) (A M)' y - (A M) (M' c) ||_2,\n
+            where "M" is a right-preconditioner for A. Under typical
+            parameter settings, the condition number of A M is <= 10.
+            """
+        return (y_star.cpu().numpy() if host else y_star), log
+
+    exec = __call__

@@ -182,6 +182,34 @@ def lsqr_ridge(sd, xw, ub, zss, sc=None, sa=1.0, su=0.0, istop=None):
     _lib.check(rc, "pla_lsqr_ridge_f64")
 
 
+def lsqr_under_init(cpc, u, atol, btol, conlim, iter_lim, dstate, istate):
+    _lib.check(_lib.load().pla_lsqr_under_init_f64(u.numel(), cpc.data_ptr(), u.data_ptr(), float(atol), float(btol),
+                                                   float(conlim), int(iter_lim), dstate.data_ptr(), istate.data_ptr(),
+                                                   _stream()), "pla_lsqr_under_init_f64")
+
+
+def lsqr_under_init2(nz, zss, dstate, istate):
+    _lib.check(_lib.load().pla_lsqr_under_init2_f64(nz, zss.data_ptr(), dstate.data_ptr(), istate.data_ptr(), _stream()),
+               "pla_lsqr_under_init2_f64")
+
+
+def lsqr_under_head(t, u, dstate, istate):
+    _lib.check(_lib.load().pla_lsqr_under_head_f64(u.numel(), t.data_ptr(), u.data_ptr(), dstate.data_ptr(),
+                                                   istate.data_ptr(), _stream()), "pla_lsqr_under_head_f64")
+
+
+def lsqr_under_tail(nz, zss, dstate, istate, hist):
+    _lib.check(_lib.load().pla_lsqr_under_tail_f64(nz, zss.data_ptr(), dstate.data_ptr(), istate.data_ptr(),
+                                                   hist.data_ptr(), _stream()), "pla_lsqr_under_tail_f64")
+
+
+def lsqr_under_long(vt, x, w, dstate, istate, itn, add_to_ww=False):
+    ws = Workspace.get(vt.device, 8 * 4 * 148 * 4, "lsqr_long")
+    _lib.check(_lib.load().pla_lsqr_under_long_f64(vt.numel(), vt.data_ptr(), x.data_ptr(), w.data_ptr(),
+                                                   dstate.data_ptr(), istate.data_ptr(), int(itn), 1 if add_to_ww else 0,
+                                                   ws.data_ptr(), ws.numel(), _stream()), "pla_lsqr_under_long_f64")
+
+
 def sumsq(x, out=None):
     lib = _lib.load()
     x = _vec(x, "x")

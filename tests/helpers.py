@@ -53,6 +53,7 @@ def sjlt_from_fixture(fx, d, m):
 SPO_FIXTURES = ["spo_sjlt_qr_600x40", "spo_sjlt_svd_600x40", "spo_sjlt_chol_600x40", "spo_sjlt_qr_ridge_600x40",
                 "spo_sjlt_svd_ridge_600x40", "spo_gauss_qr_500x37", "spo_sjlt_qr_cond1e5_2000x64",
                 "spo_sjlt_qr_odd_1531x77"]
+SPU_FIXTURES = ["spu1_sjlt_800x50", "spu1_sjlt_2000x96"]
 LOWRANK_FIXTURES = ["svd1_qb1_200x50", "svd1_qb2_200x50", "svd1_qb2_tol_200x50", "svd1_qb1_over_50x200", "evd1_qb1_120"]
 
 
@@ -65,3 +66,12 @@ class Replay:
     def __call__(self, n_rows, n_cols, rng):
         assert self.S.shape == (n_rows, n_cols)
         return self.S
+
+
+def spu_problem_from_fixture(fx):
+    rng = np.random.default_rng(int(fx["seed"]))
+    m, n = int(fx["m"]), int(fx["n"])
+    A = rng.standard_normal((m, n)) * np.logspace(0, np.log10(float(fx["cond"])), n)
+    c = rng.standard_normal(n)
+    assert digest(A) == str(fx["A_sha"]) and digest(c) == str(fx["c_sha"])
+    return A, c

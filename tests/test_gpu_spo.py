@@ -11,7 +11,8 @@ import pytest
 import torch
 
 from oracle import parla_oracle as orc
-from tests.helpers import SPO_FIXTURES, Replay, load_golden, problem_from_fixture, sjlt_from_fixture
+from tests.helpers import (SPO_FIXTURES, SPU_FIXTURES, Replay, load_golden, problem_from_fixture, sjlt_from_fixture,
+                           spu_problem_from_fixture)
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings("ignore")
@@ -179,3 +180,40 @@ def test_spo_full_size_properties(rla):
     assert float(torch.linalg.vector_norm(x - x0)) <= 10 * 0.1 * np.sqrt(n / m) * np.sqrt(n)
     assert 20 <= log.iters <= 60 and log.errors[-1] <= 1e-9 * log.errors[0]
     assert log.passes_over_A <= log.iters + 4
+
+
+@pytest.mark.parametrize("name", SPU_FIXTURES)
+def test_spu1_matches_reference_fixture(rla, name):
+    """Under-determined least squares min |y| s.t. A'y = c (SPU1, least_squares.py:425-494) with the
+    reference's sketching operator replayed."""
+    fx = load_golden(name)
+    A, c = spu_problem_from_fixture(fx)
+    m, n = A.shape
+    S = sjlt_from_fixture(fx, int(float(fx["sf"]) * n), m)
+    y, log = rla.SPU1(Replay(S), float(fx["sf"]))(dev(A), dev(c), float(fx["tol"]), int(fx["iter_lim"]), None)
+    y = y.cpu().numpy()
+    step = max(1, m // 64)
+    assert np.linalg.norm(y[::step] - fx["y_probe"]) <= 1e-9 * float(fx["y_norm"])
+    assert abs(np.linalg.norm(y) - float(fx["y_norm"])) <= 1e-9 * float(fx["y_norm"])
+    assert abs(log.errors.size - fx["errors"].size) <= 1
+    k = min(log.errors.size, fx["errors"].size)
+    assert np.allclose(log.errors[:k], fx["errors"][:k], rtol=1e-5, atol=1e-10 * fx["errors"][0])
+    # properties (test_underdet_least_squares.py:50-74): constraint satisfied, minimum norm
+    y_opt = np.linalg.lstsq(A.T, c, rcond=None)[0]
+    assert np.linalg.norm(A.T @ y - c) <= 1e-6 * np.linalg.norm(c)
+    assert np.linalg.norm(y - y_opt) <= 1e-6 * np.linalg.norm(y_opt)
+
+
+def test_pcss2_underdetermined_with_ridge(rla):
+    """saddle.py:203-214 with delta > 0: x = (A'y - c)/delta solves the regularised saddle system."""
+    rng = np.random.default_rng(12)
+    m, n, delta = 1500, 60, 0.7
+    A = rng.standard_normal((m, n)); c = rng.standard_normal(n)
+    S = orc.sjlt_operator(4 * n, m, np.random.default_rng(2), 8)
+    A_ske = np.vstack([S @ A, np.sqrt(delta) * np.eye(n)])
+    M = orc.svd_right_precond(A_ske)[0]
+    x_ref, y_ref, errs_ref = orc.pcss2_underdetermined(A, c, delta, 1e-12, 200, M, False)
+    x, y, errs = rla.PcSS2()(dev(A), None, dev(c), delta, 1e-12, 200, dev(M), False, None)
+    assert np.linalg.norm(y.cpu().numpy() - y_ref) <= 1e-9 * np.linalg.norm(y_ref)
+    assert np.linalg.norm(x.cpu().numpy() - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
+    assert abs(len(errs) - len(errs_ref)) <= 1
