@@ -236,6 +236,165 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
     }
 }
 
+// ---- Gaussian sketch, dedicated tile shape -------------------------------------------------------
+// out[M x N] (+)= G(seed)[M x K] * B[K x N] with a 64 x 256 x 16 CTA tile (8 warps side by side, warp
+// tile 64 x 32): the generated 64 x 16 operator tile is amortised over 256 output columns, i.e. half
+// the Philox / Box-Muller work per FMA of the square 128 x 128 tile, and one Philox block per thread
+// per k-step hides completely behind the DMMA groups.
+constexpr int GS_BM = 64, GS_BN = 256, GS_STAGES = 4;
+constexpr int GS_LDX = GS_BN + 4;                               // 260: 4c + r distinct mod 16
+constexpr int GS_TILE_A = GS_BM * GM_LDK, GS_TILE_B = GM_BK * GS_LDX;
+
+template <bool VEC16>
+__device__ __forceinline__ void gs_load_b(double* tile, const double* __restrict__ src, long long ld, long long X,
+                                          long long K, long long x0, long long k0, const double* __restrict__ xcol) {
+    const int tid = threadIdx.x;
+    if (VEC16) {                       // 16 rows x 128 chunks(16B): thread -> chunk tid&127 of rows (tid>>7) + 2 i
+        const int r0 = tid >> 7, c2 = 2 * (tid & 127);
+        const long long gx = x0 + c2;
+        const bool xok = gx < X;
+        const bool extra = (xcol != nullptr) && (gx == X);
+        const double* p = src + (k0 + r0) * ld + gx;
+        double* d = tile + r0 * GS_LDX + c2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool kok = k0 + r0 + 2 * i < K;
+            if (!extra) {
+                const bool ok = xok && kok;
+                cp_async16(d + 2 * i * GS_LDX, ok ? p + 2 * i * ld : src, ok);
+            } else {
+                cp_async8(d + 2 * i * GS_LDX, kok ? xcol + k0 + r0 + 2 * i : src, kok);
+                cp_async8(d + 2 * i * GS_LDX + 1, src, false);
+            }
+        }
+    } else {                           // 16 rows x 256 doubles: thread -> column tid of rows i
+        const long long gx = x0 + tid;
+        const bool xok = gx < X;
+        const bool extra = (xcol != nullptr) && (gx == X);
+        const double* p = src + k0 * ld + gx;
+        double* d = tile + tid;
+#pragma unroll
+        for (int i = 0; i < GM_BK; ++i) {
+            const bool kok = k0 + i < K;
+            if (!extra) {
+                const bool ok = xok && kok;
+                cp_async8(d + i * GS_LDX, ok ? p + i * ld : src, ok);
+            } else {
+                cp_async8(d + i * GS_LDX, kok ? xcol + k0 + i : src, kok);
+            }
+        }
+    }
+}
+
+// operator-tile generation in two phases: (1) Philox rounds -> 4 words in registers, (2) Box-Muller + store
+__device__ __forceinline__ Philox4 gs_gen_words(uint64_t seed, long long col_offset, long long x0, long long k0) {
+    const int tid = threadIdx.x;                      // 64 rows x 4 quads: one Philox block per thread
+    const long long gx = x0 + (tid >> 2), gk = k0 + 4 * (tid & 3);
+    const uint64_t q = (uint64_t)(col_offset + gk) >> 2;
+    return philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)gx, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+__device__ __forceinline__ void gs_store_a(double* tile, const Philox4& words, long long X, long long K, long long x0,
+                                           long long k0) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 2, qd = tid & 3;
+    const long long gx = x0 + r, gk = k0 + 4 * qd;
+    double g[4] = {0.0, 0.0, 0.0, 0.0};
+    if (gx < X && gk < K) {
+        philox_words_to_normal4(words, g);
+        if (gk + 4 > K) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (gk + j >= K) g[j] = 0.0;
+        }
+    }
+    double* dst = tile + r * GM_LDK + 4 * qd;
+    *reinterpret_cast<double2*>(dst) = make_double2(g[0], g[1]);
+    *reinterpret_cast<double2*>(dst + 2) = make_double2(g[2], g[3]);
+}
+
+template <bool VEC16>
+__global__ void __launch_bounds__(GM_THREADS, 1) gauss_sketch_kernel(const GemmParams p) {
+    extern __shared__ __align__(16) double gm_smem[];
+    double* sA = gm_smem;                               // [STAGES][GS_TILE_A]
+    double* sB = gm_smem + GS_STAGES * GS_TILE_A;       // [STAGES][GS_TILE_B]
+    const int tid = threadIdx.x, lane = tid & 31, wn = tid >> 5;     // 8 warps along N
+    const long long m0 = (long long)blockIdx.y * GS_BM, n0 = (long long)blockIdx.x * GS_BN;
+    const long long ktiles = (p.K + GM_BK - 1) / GM_BK;
+    const long long kt_begin = (long long)blockIdx.z * p.ktiles_per_split;
+    long long kt_end = kt_begin + p.ktiles_per_split;
+    if (kt_end > ktiles) kt_end = ktiles;
+    const int nkt = (int)(kt_end - kt_begin);
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    Philox4 words{0u, 0u, 0u, 0u};
+    auto gen_words = [&](int kt_local) { words = gs_gen_words(p.seed, p.col_offset, m0, (kt_begin + kt_local) * GM_BK); };
+    auto gen_store = [&](int kt_local) {
+        gs_store_a(sA + (kt_local % GS_STAGES) * GS_TILE_A, words, p.M, p.K, m0, (kt_begin + kt_local) * GM_BK);
+    };
+    auto issue_a = [&](int kt_local) { gen_words(kt_local); gen_store(kt_local); };
+    // (staggering the generation between the two warps of a scheduler, or splitting it further across
+    //  k-steps with run-time phases, measured slower: 25.8 vs 27.1 TF -- the extra branches cost more)
+    auto issue_b = [&](int kt_local) {
+        gs_load_b<VEC16>(sB + (kt_local % GS_STAGES) * GS_TILE_B, p.B, p.ldb, p.Nb, p.K, n0,
+                         (kt_begin + kt_local) * GM_BK, p.xcol);
+    };
+#pragma unroll
+    for (int s = 0; s < GS_STAGES - 1; ++s) {
+        if (s < nkt) { issue_a(s); issue_b(s); }
+        cp_async_commit();
+    }
+    const int fr = lane >> 2, fc = lane & 3;
+    for (int kt = 0; kt < nkt; ++kt) {
+        cp_async_wait<GS_STAGES - 2>();
+        __syncthreads();
+        const double* a = sA + (kt % GS_STAGES) * GS_TILE_A;
+        const double* b = sB + (kt % GS_STAGES) * GS_TILE_B;
+        const bool more = kt + GS_STAGES - 1 < nkt;
+#pragma unroll
+        for (int kk = 0; kk < GM_BK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = a[(i * 8 + fr) * GM_LDK + kk + fc];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = b[(kk + fc) * GS_LDX + wn * 32 + j * 8 + fr];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            if (kk == 0 && more) issue_b(kt + GS_STAGES - 1);
+            if (kk == 0) cp_async_commit();
+            if (kk == 4 && more) gen_words(kt + GS_STAGES - 1);
+            if (kk == 8 && more) gen_store(kt + GS_STAGES - 1);
+        }
+    }
+    cp_async_wait<0>();
+
+    const bool split = p.part != nullptr;
+    double* out = split ? p.part + (size_t)blockIdx.z * p.M * p.N : p.C;
+    const long long ldo = split ? p.N : p.ldc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long gm = m0 + i * 8 + fr;
+        if (gm >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long gn = n0 + wn * 32 + j * 8 + 2 * fc;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (gn + e < p.N) {
+                    double* dst = out + gm * ldo + gn + e;
+                    if (split) *dst = acc[i][j][e];
+                    else *dst = (p.beta == 0.0) ? p.alpha * acc[i][j][e] : fma(p.alpha, acc[i][j][e], p.beta * *dst);
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) gemm_splitk_reduce(const double* __restrict__ part, int splits, long long M,
                                                           long long N, double alpha, double beta, double* C,
                                                           long long ldc) {
@@ -334,6 +493,58 @@ __global__ void __launch_bounds__(256) gauss_matvec_reduce(const double* __restr
     out[r * ldo] = (beta == 0.0) ? scale * acc : fma(scale, acc, beta * out[r * ldo]);
 }
 
+static int choose_splits_tiles(long long tiles, long long K) {
+    const long long ktiles = (K + GM_BK - 1) / GM_BK;
+    const long long sms = num_sms();
+    if (tiles >= 4 * sms || ktiles < 64) return 1;
+    long long smax = ktiles / 32;
+    if (smax > 64) smax = 64;
+    int best = 1;
+    double best_eff = (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);
+    for (long long sp = 2; sp <= smax; ++sp) {
+        const long long ctas = tiles * sp;
+        const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = (int)sp; }
+        if (ctas >= 8 * sms) break;
+    }
+    return best;
+}
+
+static int launch_gauss(GemmParams& p, void* ws, size_t ws_bytes, bool vec16, cudaStream_t st) {
+    const long long tiles = ((p.M + GS_BM - 1) / GS_BM) * ((p.N + GS_BN - 1) / GS_BN);
+    const int splits = choose_splits_tiles(tiles, p.K);
+    const long long ktiles = (p.K + GM_BK - 1) / GM_BK;
+    p.ktiles_per_split = (int)((ktiles + splits - 1) / splits);
+    const int zs = (int)((ktiles + p.ktiles_per_split - 1) / p.ktiles_per_split);
+    p.part = nullptr;
+    if (zs > 1) {
+        const size_t need = (size_t)zs * p.M * p.N * sizeof(double);
+        if (ws == nullptr || ws_bytes < need) { set_error("sketch_gauss: workspace too small (%zu < %zu)", ws_bytes, need); return -13; }
+        p.part = (double*)ws;
+    }
+    dim3 grid((unsigned)((p.N + GS_BN - 1) / GS_BN), (unsigned)((p.M + GS_BM - 1) / GS_BM), (unsigned)zs);
+    const size_t smem = (size_t)GS_STAGES * (GS_TILE_A + GS_TILE_B) * sizeof(double);
+    cudaError_t e;
+    if (vec16) {
+        e = cudaFuncSetAttribute(gauss_sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) { gauss_sketch_kernel<true><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); note_launch(); }
+    } else {
+        e = cudaFuncSetAttribute(gauss_sketch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) { gauss_sketch_kernel<false><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); note_launch(); }
+    }
+    if (e != cudaSuccess) { set_error("sketch_gauss: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    if (zs > 1) {
+        long long total = p.M * p.N;
+        int nb = (int)((total + 255) / 256);
+        if (nb > 4 * num_sms()) nb = 4 * num_sms();
+        gemm_splitk_reduce<<<nb, 256, 0, st>>>(p.part, zs, p.M, p.N, p.alpha, p.beta, p.C, p.ldc);
+        e = cudaGetLastError();
+        note_launch();
+        if (e != cudaSuccess) { set_error("sketch_gauss: reduce launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    return 0;
+}
+
 static bool aligned16(const void* ptr, long long ld) { return ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld % 2 == 0); }
 
 }  // namespace pla
@@ -369,9 +580,14 @@ extern "C" int pla_gemm_f64(int transa, int transb, int64_t M, int64_t N, int64_
 }
 
 extern "C" size_t pla_sketch_gauss_workspace_bytes(int64_t d, int64_t n, int64_t m) {
-    size_t a = pla_gemm_workspace_bytes(d, n + 1, m), b = pla_gemm_workspace_bytes(d, n, m);
-    size_t c = (size_t)d * 8 * 64;                    // k-split partials of the separate rhs sketch
-    return (a > b ? a : b) > c ? (a > b ? a : b) : c;
+    size_t best = (size_t)d * 8 * 64;                 // k-split partials of the separate rhs sketch
+    for (int64_t nn = n; nn <= n + 1; ++nn) {
+        const long long tiles = ((d + GS_BM - 1) / GS_BM) * ((nn + GS_BN - 1) / GS_BN);
+        const int sp = choose_splits_tiles(tiles, m);
+        const size_t need = sp > 1 ? (size_t)sp * d * nn * sizeof(double) : 0;
+        if (need > best) best = need;
+    }
+    return best;
 }
 
 extern "C" int pla_sketch_gauss_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* bvec, int64_t d,
@@ -387,14 +603,14 @@ extern "C" int pla_sketch_gauss_f64(const double* A, int64_t m, int64_t n, int64
     cudaStream_t st = (cudaStream_t)stream;
     // The rhs rides as an extra logical column of A unless that would open a whole new 128-column
     // tile (n a multiple of 128): then S @ b is a separate generate-and-dot kernel (~1 % of the work).
-    const bool separate_b = (bvec != nullptr) && (n % GM_BN == 0) && (m % 4 == 0);
+    const bool separate_b = (bvec != nullptr) && (n % GS_BN == 0) && (m % 4 == 0);
     GemmParams p;
     p.A = nullptr; p.lda = 0; p.B = A; p.ldb = lda; p.C = out; p.ldc = ldo; p.M = d; p.K = m;
     p.N = separate_b ? n : ncols;
     p.Nb = n; p.xcol = separate_b ? nullptr : bvec;
     p.alpha = scale; p.beta = beta; p.seed = seed; p.col_offset = col_offset; p.part = nullptr;
     const bool vec16 = aligned16(A, lda) && (n % 2 == 0);
-    int rc = launch_gemm<2, 0>(p, ws, ws_bytes, vec16, st);
+    int rc = launch_gauss(p, ws, ws_bytes, vec16, st);
     if (rc != 0 || !separate_b) return rc;
     // workspace is free again once the GEMM (and its split-K reduce) are enqueued on the same stream
     int splits = (int)((4LL * num_sms() * 8 + d - 1) / d);

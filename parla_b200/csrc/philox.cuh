@@ -26,6 +26,25 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 }
 
 #ifdef __CUDACC__
+// Box-Muller on the four words of one Philox block (second half of philox_normal4, split out so the
+// integer rounds and the transcendental part can be issued at different points of a DMMA loop).
+__device__ __forceinline__ void philox_words_to_normal4(const Philox4& o, double out[4]) {
+    const float s = 2.3283064365386963e-10f;   // 2^-32
+    const float ua = fmaf((float)o.x, s, 0.5f * s);
+    const float ub = fmaf((float)o.y, s, 0.5f * s);
+    const float uc = fmaf((float)o.z, s, 0.5f * s);
+    const float ud = fmaf((float)o.w, s, 0.5f * s);
+    const float ra = sqrtf(-2.0f * __logf(fminf(ua, 1.0f)));
+    const float rc = sqrtf(-2.0f * __logf(fminf(uc, 1.0f)));
+    float sa, ca, sc, cc;
+    __sincosf(3.14159265358979f * (2.0f * ub - 1.0f), &sa, &ca);
+    __sincosf(3.14159265358979f * (2.0f * ud - 1.0f), &sc, &cc);
+    out[0] = (double)(ra * ca);
+    out[1] = (double)(ra * sa);
+    out[2] = (double)(rc * cc);
+    out[3] = (double)(rc * sc);
+}
+
 // Four standard normals for operator row r, column block q (columns 4q .. 4q+3).
 // u = (o + 0.5) 2^-32 in (0,1); Box-Muller with fp32 fast intrinsics, widened to fp64.
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t r, uint64_t q, double out[4]) {
