@@ -15,6 +15,17 @@ from ...parallel import allreduce_
 
 F64 = torch.float64
 POLL_LAG = 2      # iterations the host may run ahead of the device-side stopping test
+_POLL_CACHE = {}
+
+
+def _poll_buffers():
+    """Pinned mirrors of the device-side LSQR flags + their events (allocated once per process:
+    cudaHostAlloc is far slower than an LSQR iteration on small problems)."""
+    key = torch.cuda.current_device()
+    if key not in _POLL_CACHE:
+        _POLL_CACHE[key] = ([torch.zeros(K.LSQR_NINT, dtype=torch.int32).pin_memory() for _ in range(POLL_LAG + 1)],
+                            [torch.cuda.Event() for _ in range(POLL_LAG + 1)])
+    return _POLL_CACHE[key]
 
 
 def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=False, calc_var=False,
@@ -53,8 +64,7 @@ def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=F
 
     sc = dstate[K.LSQR_SA:K.LSQR_SA + 2]
     istop_dev = istate[0:1]
-    pinned = [torch.zeros(K.LSQR_NINT, dtype=torch.int32).pin_memory() for _ in range(POLL_LAG + 1)]
-    events = [torch.cuda.Event() for _ in range(POLL_LAG + 1)]
+    pinned, events = _poll_buffers()
 
     def post(slot):
         pinned[slot].copy_(istate, non_blocking=True)
@@ -131,8 +141,7 @@ def lsqr_adjoint(A, c_pc, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None):
     K.lsqr_under_init2(nA, zss, dstate, istate)
     long_update(0)
 
-    pinned = [torch.zeros(K.LSQR_NINT, dtype=torch.int32).pin_memory() for _ in range(POLL_LAG + 1)]
-    events = [torch.cuda.Event() for _ in range(POLL_LAG + 1)]
+    pinned, events = _poll_buffers()
 
     def post(slot):
         pinned[slot].copy_(istate, non_blocking=True)

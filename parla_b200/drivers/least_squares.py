@@ -234,7 +234,8 @@ class SPO(OverLstsqSolver):
                     t=torch.empty(R.shape[1], dtype=F64, device=dev))
         xw = torch.empty(n, dtype=F64, device=dev)
         op.bidiag_pass(z_ske, warm["u"], warm["ub"], warm["zss"], xw, warm["t"], sa=-1.0, su=1.0)
-        rel_err = math.sqrt(float(warm["zss"][n])) / bnorm
+        with np.errstate(divide='ignore', invalid='ignore'):       # b == 0 gives nan, as in the reference (:347)
+            rel_err = float(np.float64(math.sqrt(float(warm["zss"][n]))) / np.float64(bnorm))
         if rel_err >= 1 or (rel_err > 1e-15 and R.shape[0] != R.shape[1]):
             # Either the zero vector is a better solution, or we have an inconsistent
             # rank-deficient problem (which forces us to initialize at the origin).

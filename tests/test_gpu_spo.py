@@ -217,3 +217,21 @@ def test_pcss2_underdetermined_with_ridge(rla):
     assert np.linalg.norm(y.cpu().numpy() - y_ref) <= 1e-9 * np.linalg.norm(y_ref)
     assert np.linalg.norm(x.cpu().numpy() - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
     assert abs(len(errs) - len(errs_ref)) <= 1
+
+
+def test_spo_degenerate_inputs(rla):
+    """b = 0 (LSQR's alfa*beta == 0 early exit, lsqr.py:392-395), a single column, iter_lim = 1, loose tol."""
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((400, 12))
+    x, log = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(dev(A), dev(np.zeros(400)), 0.0, 1e-12, 50, 1)
+    assert float(x.abs().max()) == 0.0 and log.errors.shape == (2,)
+    a1 = rng.standard_normal((300, 1)); b1 = rng.standard_normal(300)
+    x, log = rla.SPO(rla.SkOpGA(), 4, 'qr')(dev(a1), dev(b1), 0.0, 1e-12, 50, 1)
+    assert abs(float(x[0]) - float(a1[:, 0] @ b1 / (a1[:, 0] @ a1[:, 0]))) < 1e-12
+    b = rng.standard_normal(400)
+    x, log = rla.SPO(rla.SkOpSJ(8), 4, 'svd')(dev(A), dev(b), 0.0, 1e-12, 1, 1)       # one iteration only
+    assert log.errors.size == 2
+    x, log = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(dev(A), dev(b), 0.0, 0.5, 50, 1)         # loose tolerance stops early
+    assert log.errors.size - 1 <= 3
+    xs, _ = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(dev(A), dev(b), 0.0, 1e-12, 50, 1, logging=False)
+    assert np.linalg.norm(xs.cpu().numpy() - np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-10
