@@ -13,14 +13,17 @@
 
 namespace pla {
 
-constexpr int SP_GROUP = 256;         // consumer threads per group (8 warps)
+constexpr int SP_GROUP_MAX = 256;     // consumer threads per group: 256 (8 warps) or, for narrow A, 128
 constexpr int SP_RMAX = 8;            // max rows per tile
 constexpr int SP_MAX_STAGES = 8;
-constexpr int SP_MAX_GROUPS = 2;
+constexpr int SP_MAX_GROUPS = 4;
 
 // rows per tile as a function of the column-ownership shape: ~32 KB tiles, R*n even for odd n
-template <int VEC, int J> struct SpRows {
-    static constexpr int value = VEC == 2 ? (J >= 8 ? 1 : 8 / J) : (J <= 2 ? 8 : (J == 4 ? 4 : 2));
+template <int VEC, int J, int GS> struct SpRows {
+    static constexpr int cols = VEC * J * GS;                 // widest matrix this shape serves
+    static constexpr int raw = 4096 / cols;                   // rows of a ~32 KB tile
+    static constexpr int capped = raw < 1 ? 1 : (raw > 8 ? 8 : raw);
+    static constexpr int value = (VEC == 1 && capped == 1) ? 2 : capped;   // odd n needs an even row count
 };
 
 struct StreamPassParams {
@@ -42,10 +45,11 @@ struct StreamPassParams {
 
 // NG independent consumer groups per CTA take alternate tiles of the CTA's sequence, so the
 // dot -> reduce -> barrier -> axpy latency chain of one tile overlaps with the other group's.
-template <int VEC, int J, int NG>
-__global__ void __launch_bounds__(NG * SP_GROUP + 32, 1) stream_pass_kernel(const StreamPassParams p) {
+template <int VEC, int J, int NG, int GS>
+__global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const StreamPassParams p) {
     if (p.istop != nullptr && *p.istop != 0) return;
-    constexpr int RT = SpRows<VEC, J>::value;
+    constexpr int SP_GROUP = GS;
+    constexpr int RT = SpRows<VEC, J, GS>::value;
     constexpr int NCONS = NG * SP_GROUP;
     constexpr int NW = SP_GROUP / 32;
     extern __shared__ __align__(128) unsigned char sp_smem[];
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(NG * SP_GROUP + 32, 1) stream_pass_kernel(cons
     uint64_t* full = reinterpret_cast<uint64_t*>(sp_smem + off);
     uint64_t* empty = full + SP_MAX_STAGES;
     double* red = reinterpret_cast<double*>(empty + SP_MAX_STAGES);     // [groups][2][8 warps][RMAX]
-    double* ustage = red + SP_MAX_GROUPS * 2 * NW * SP_RMAX;            // [stages][RMAX]  old u of the tile rows
+    double* ustage = red + SP_MAX_GROUPS * 2 * (SP_GROUP_MAX / 32) * SP_RMAX;   // [stages][RMAX]  old u of the tile rows
     double* gstage = ustage + SP_MAX_STAGES * SP_RMAX;                  // [stages][RMAX]  g of the tile rows
 
     if (tid == 0) {
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(NG * SP_GROUP + 32, 1) stream_pass_kernel(cons
 #pragma unroll
                 for (int r = 0; r < RT; ++r) myred[wid * SP_RMAX + r] = dot[r];
             }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(SP_GROUP) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GS) : "memory");
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
                 double tot = 0.0;
@@ -271,9 +275,9 @@ __global__ void __launch_bounds__(256) stream_pass_reduce_kernel(const double* _
     }
 }
 
-template <int VEC, int J, int NG>
+template <int VEC, int J, int NG, int GS>
 static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts) {
-    constexpr int RT = SpRows<VEC, J>::value;
+    constexpr int RT = SpRows<VEC, J, GS>::value;
     const size_t stage_bytes = (size_t)RT * p.n * 8;
     const size_t budget = 200 * 1024;
     int stages = (int)(budget / stage_bytes);
@@ -286,11 +290,11 @@ static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts
     if ((long long)grid > p.ntiles) grid = (int)p.ntiles;
     *nparts = grid * NG;
     const size_t smem = (((size_t)stages * stage_bytes + 15) & ~(size_t)15) + 2 * SP_MAX_STAGES * 8 +
-                        SP_MAX_GROUPS * 2 * (SP_GROUP / 32) * SP_RMAX * 8 + 2 * SP_MAX_STAGES * SP_RMAX * 8;
-    cudaError_t e = cudaFuncSetAttribute(stream_pass_kernel<VEC, J, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        SP_MAX_GROUPS * 2 * (SP_GROUP_MAX / 32) * SP_RMAX * 8 + 2 * SP_MAX_STAGES * SP_RMAX * 8;
+    cudaError_t e = cudaFuncSetAttribute(stream_pass_kernel<VEC, J, NG, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    stream_pass_kernel<VEC, J, NG><<<grid, NG * SP_GROUP + 32, smem, st>>>(p);
+    stream_pass_kernel<VEC, J, NG, GS><<<grid, NG * GS + 32, smem, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }
@@ -300,7 +304,7 @@ static int sp_groups() {
     if (v == 0) {
         const char* e = getenv("PLA_PASS_GROUPS");
         v = e ? atoi(e) : 2;
-        if (v < 1 || v > SP_MAX_GROUPS) v = 2;
+        if (v < 1 || v > 2) v = 2;
     }
     return v;
 }
@@ -333,7 +337,11 @@ extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_
     p.A = A; p.m = m; p.n = n; p.lda = lda; p.w = w; p.u = u; p.g = g; p.sc = sc_dev; p.sa = sa; p.su = su;
     p.istop = istop_dev; p.flags = flags;
     const int vec = (n % 2 == 0) ? 2 : 1;
-    const long long groups = (n + (long long)vec * SP_GROUP - 1) / ((long long)vec * SP_GROUP);
+    // Narrow matrices (<= 1024 columns when even, <= 512 when odd): four groups of 128 threads, so four
+    // tiles are in flight per SM and the per-tile reduce/barrier latency stays hidden.  Wider: groups of 256.
+    const bool narrow = n <= (long long)vec * 4 * 128 && sp_groups() == 2;
+    const int gs = narrow ? 128 : 256;
+    const long long groups = (n + (long long)vec * gs - 1) / ((long long)vec * gs);
     PLA_CHECK_ARG(groups <= 16, 3, "n too large for this vector width (odd n must be <= 4096)");
     p.zpart = reinterpret_cast<double*>(ws);
     p.sspart = p.zpart + (size_t)num_sms() * SP_MAX_GROUPS * n;
@@ -341,19 +349,29 @@ extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_
 
     cudaError_t e;
     int nparts = 0;
-#define PLA_SP_CASE(V, JJ, NGG) e = launch_pass<V, JJ, NGG>(p, st, &nparts)
-    if (vec == 2) {
-        if (groups <= 1) { if (two) PLA_SP_CASE(2, 1, 2); else PLA_SP_CASE(2, 1, 1); }
-        else if (groups <= 2) { if (two) PLA_SP_CASE(2, 2, 2); else PLA_SP_CASE(2, 2, 1); }
-        else if (groups <= 4) { if (two) PLA_SP_CASE(2, 4, 2); else PLA_SP_CASE(2, 4, 1); }
-        else if (groups <= 8) PLA_SP_CASE(2, 8, 1);
-        else PLA_SP_CASE(2, 16, 1);
+#define PLA_SP_CASE(V, JJ, NGG, GSS) e = launch_pass<V, JJ, NGG, GSS>(p, st, &nparts)
+    if (narrow) {
+        if (vec == 2) {
+            if (groups <= 1) PLA_SP_CASE(2, 1, 4, 128);
+            else if (groups <= 2) PLA_SP_CASE(2, 2, 4, 128);
+            else PLA_SP_CASE(2, 4, 4, 128);
+        } else {
+            if (groups <= 1) PLA_SP_CASE(1, 1, 4, 128);
+            else if (groups <= 2) PLA_SP_CASE(1, 2, 4, 128);
+            else PLA_SP_CASE(1, 4, 4, 128);
+        }
+    } else if (vec == 2) {
+        if (groups <= 1) { if (two) PLA_SP_CASE(2, 1, 2, 256); else PLA_SP_CASE(2, 1, 1, 256); }
+        else if (groups <= 2) { if (two) PLA_SP_CASE(2, 2, 2, 256); else PLA_SP_CASE(2, 2, 1, 256); }
+        else if (groups <= 4) { if (two) PLA_SP_CASE(2, 4, 2, 256); else PLA_SP_CASE(2, 4, 1, 256); }
+        else if (groups <= 8) PLA_SP_CASE(2, 8, 1, 256);
+        else PLA_SP_CASE(2, 16, 1, 256);
     } else {
-        if (groups <= 1) { if (two) PLA_SP_CASE(1, 1, 2); else PLA_SP_CASE(1, 1, 1); }
-        else if (groups <= 2) { if (two) PLA_SP_CASE(1, 2, 2); else PLA_SP_CASE(1, 2, 1); }
-        else if (groups <= 4) { if (two) PLA_SP_CASE(1, 4, 2); else PLA_SP_CASE(1, 4, 1); }
-        else if (groups <= 8) PLA_SP_CASE(1, 8, 1);
-        else PLA_SP_CASE(1, 16, 1);
+        if (groups <= 1) { if (two) PLA_SP_CASE(1, 1, 2, 256); else PLA_SP_CASE(1, 1, 1, 256); }
+        else if (groups <= 2) { if (two) PLA_SP_CASE(1, 2, 2, 256); else PLA_SP_CASE(1, 2, 1, 256); }
+        else if (groups <= 4) { if (two) PLA_SP_CASE(1, 4, 2, 256); else PLA_SP_CASE(1, 4, 1, 256); }
+        else if (groups <= 8) PLA_SP_CASE(1, 8, 1, 256);
+        else PLA_SP_CASE(1, 16, 1, 256);
     }
 #undef PLA_SP_CASE
     if (e != cudaSuccess) { set_error("pla_stream_pass_f64: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
