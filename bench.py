@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 
 TOL, ITER_LIM, SF, VEC_NNZ = 1e-12, 100, 4, 8
 METRIC, UNIT = "sap1_lsq_solve_time_2^22x2048_fp64", "s"
+MODE = "qr"
 
 
 def parse():
@@ -38,6 +39,7 @@ def parse():
     ap.add_argument("--m", type=int, default=1 << 22, help="rows per GPU")
     ap.add_argument("--n", type=int, default=2048)
     ap.add_argument("--sketch", default="sjlt", choices=["sjlt", "gauss"])
+    ap.add_argument("--mode", default="qr", choices=["qr", "svd", "chol"], help="SPO preconditioner: qr = SAP1, svd = SAP2")
     ap.add_argument("--cpu-rows", type=int, default=1 << 16, help="rows of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -45,7 +47,7 @@ def parse():
 
 
 def workload_name(a, world):
-    return (f"SAP1/SPO(mode=qr) overdetermined least squares, {a.m}x{a.n} fp64 per GPU "
+    return (f"{'SAP1' if a.mode == 'qr' else 'SAP2' if a.mode == 'svd' else 'SPO'}/SPO(mode={a.mode}) overdetermined least squares, {a.m}x{a.n} fp64 per GPU "
             f"(m_global={a.m * world}), {a.sketch.upper()} sketch"
             f"{' k=8' if a.sketch == 'sjlt' else ''}, d=4n={SF * a.n}, tol=1e-12, iter_lim=100 "
             f"[BASELINE.json configs[1]]")
@@ -60,7 +62,7 @@ def cpu_solve_sample(n, rows, seed=0):
     rng = np.random.default_rng(seed)
     A = rng.standard_normal((rows, n))
     b = A @ rng.standard_normal(n) + 0.1 * rng.standard_normal(rows)
-    x, log = orc.SPO(orc.SkOpSJ(VEC_NNZ), SF, 'qr')(A, b, 0.0, TOL, ITER_LIM, np.random.default_rng(seed + 1))
+    x, log = orc.SPO(orc.SkOpSJ(VEC_NNZ), SF, MODE)(A, b, 0.0, TOL, ITER_LIM, np.random.default_rng(seed + 1))
     return dict(sketch=log.time_sketch, factor=log.time_factor, presolve=log.time_presolve,
                 iterate=log.time_iterate, iters=int(log.errors.size - 1))
 
@@ -174,7 +176,7 @@ def run_gpu_arm(a):
     b, _ = K.matvec(A, x0)
     b += 0.1 * torch.randn(m, dtype=torch.float64, device=dev, generator=g)
     gen = rla.SkOpSJ(VEC_NNZ) if a.sketch == "sjlt" else rla.SkOpGA()
-    alg = rla.SPO(gen, SF, 'qr')
+    alg = rla.SPO(gen, SF, a.mode)
     Ash = rla.RowSharded(A, rank * m, world * m) if world > 1 else A
     bsh = rla.RowSharded(b, rank * m, world * m) if world > 1 else b
 
@@ -321,6 +323,7 @@ def run_gpu_arm(a):
 
 if __name__ == "__main__":
     args = parse()
+    MODE = args.mode
     if args.impl == "reference":
         run_reference_arm(args)
     else:

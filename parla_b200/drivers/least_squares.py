@@ -205,11 +205,15 @@ class SPO(OverLstsqSolver):
             z_ske = K.trsv_upper(R, g, trans=True)
             tri = True
         elif self.mode == 'svd':
+            # SVD of the sketch through its Householder QR (same factorisation as mode 'qr'): A_ske = Q R_qr,
+            # R_qr = U_r diag(sigma) Vh  =>  svd(A_ske) = (Q U_r, sigma, Vh).  Only the n x n SVD goes to
+            # cuSOLVER, and U^T b_ske = U_r^T (Q^T b_ske) comes out of the same QR (last column of W).
             tic = quick_time()
-            R, U, sigma, Vh = rpc.svd_right_precond(W[:, :n])
+            K.geqrf(W, n)
+            R, U_r, sigma, Vh = rpc.svd_right_precond(torch.triu(W[:n, :n]))       # :330-339
             log.time_factor = quick_time() - tic
             tic = quick_time()
-            z_ske = K.rmatvec(U[:d], W[:d, n].contiguous())[:R.shape[1]].clone()
+            z_ske = K.rmatvec(U_r, W[:n, n].contiguous())[:R.shape[1]].clone()      # U[:d].T @ b_ske
             tri = False
         else:
             raise ValueError()
