@@ -36,8 +36,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--m", type=int, default=1 << 22, help="rows per GPU")
-    ap.add_argument("--n", type=int, default=2048)
+    # (--rows/--cols rather than only --m/--n: torchrun's own parser treats "--m"/"--n" as ambiguous abbreviations)
+    ap.add_argument("--rows", "--m", dest="m", type=int, default=1 << 22, help="rows per GPU")
+    ap.add_argument("--cols", "--n", dest="n", type=int, default=2048)
     ap.add_argument("--sketch", default="sjlt", choices=["sjlt", "gauss"])
     ap.add_argument("--mode", default="qr", choices=["qr", "svd", "chol"], help="SPO preconditioner: qr = SAP1, svd = SAP2")
     ap.add_argument("--cpu-rows", type=int, default=1 << 16, help="rows of the bounded CPU sample")

@@ -1,0 +1,42 @@
+"""Tiny invocation of every kernel family, meant to run under compute-sanitizer
+(memcheck / racecheck) on a B200:  compute-sanitizer --tool memcheck python scripts/sanitize_smoke.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import parla_b200 as rla                      # noqa: E402
+from parla_b200 import kernels as K           # noqa: E402
+
+rng = np.random.default_rng(0)
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+for (m, n) in ((300, 40), (513, 77), (700, 600), (64, 2050)):
+    A, w, u = rng.standard_normal((m, n)), rng.standard_normal(n), rng.standard_normal(m)
+    ud = dev(u)
+    z = K.stream_pass(dev(A), w=dev(w), u=ud, sa=0.5, su=-1.0, flags=3).cpu().numpy()
+    ur = 0.5 * (A @ w) - u
+    assert np.allclose(ud.cpu().numpy(), ur) and np.allclose(z[:n], A.T @ ur)
+R = np.linalg.qr(rng.standard_normal((150, 70)))[1]
+for tr in (False, True):
+    x = K.trsv_upper(dev(R), dev(np.ones(70)), trans=tr).cpu().numpy()
+    assert np.allclose((R.T if tr else R) @ x, 1.0)
+assert np.allclose(K.trtri_upper(dev(R)).cpu().numpy() @ R, np.eye(70), atol=1e-10)
+for ta, tb in ((0, 0), (1, 0), (0, 1), (1, 1)):
+    Am, Bm = rng.standard_normal((90, 150) if ta else (150, 90)), rng.standard_normal((70, 90) if tb else (90, 70))
+    C = K.gemm(dev(Am), dev(Bm), transa=bool(ta), transb=bool(tb)).cpu().numpy()
+    assert np.allclose(C, (Am.T if ta else Am) @ (Bm.T if tb else Bm))
+Y = rng.standard_normal((600, 40))
+Q, Rr = K.qr_economic(dev(Y))
+assert np.allclose((Q @ Rr).cpu().numpy(), Y)
+A = rng.standard_normal((900, 30)); b = rng.standard_normal(900)
+for gen in (rla.SkOpSJ(8), rla.SkOpGA()):
+    for mode, delta in (("qr", 0.0), ("svd", 0.2)):
+        x, log = rla.SPO(gen, 4, mode)(dev(A), dev(b), delta, 1e-12, 60, 1)
+        ref = np.linalg.lstsq(np.vstack([A, np.sqrt(delta) * np.eye(30)]), np.concatenate([b, np.zeros(30)]), rcond=None)[0]
+        assert np.linalg.norm(x.cpu().numpy() - ref) < 1e-9 * np.linalg.norm(ref)
+y, _ = rla.SPU1(rla.SkOpSJ(8), 4)(dev(A), dev(rng.standard_normal(30)), 1e-12, 60, 1)
+U, s, Vh = rla.SVD1(rla.QB2(rla.RF1(rla.RS1(rla.SkOpGA(), 2, rla.orth, 1)), 8, False))(dev(A), 16, 0.0, 0, 1)
+torch.cuda.synchronize()
+print("sanitize_smoke OK")
