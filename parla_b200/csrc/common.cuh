@@ -42,6 +42,25 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Sum NV (<= 32) per-lane values across the warp in one butterfly: 31 shuffles instead of 5 * NV.
+// On return lane l (< NV) holds the warp total of value l in v[0].  Fixed order => deterministic.
+template <int NV>
+__device__ __forceinline__ void warp_multi_sum(double (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = NV; i < 32; ++i) v[i] = 0.0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const double send = upper ? v[i] : v[i + off];
+            const double keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
 // Block-wide sum for blockDim.x <= 1024 (multiple of 32); result valid in every thread.
 // `scratch` must hold 33 doubles. Deterministic (fixed tree).
 __device__ __forceinline__ double block_sum(double v, double* scratch) {

@@ -80,10 +80,12 @@ __global__ void __launch_bounds__(QR_THREADS) qr_panel_kernel(const PanelParams 
 
     for (int j = 0; j < jb; ++j) {
         // ---- publish this CTA's partial sums for column j, then meet at the barrier
+        {
+            double v32[32];
 #pragma unroll
-        for (int c = 0; c < QR_NP; ++c) {
-            const double v = warp_sum(part[c]);
-            if (lane == 0) wsum[wid][c] = v;
+            for (int c = 0; c < QR_NP; ++c) v32[c] = part[c];
+            warp_multi_sum<QR_NP>(v32);
+            if (lane < QR_NP) wsum[wid][lane] = v32[0];
         }
         __syncthreads();
         double* mypart = p.gpart + ((size_t)(j & 1) * G + blockIdx.x) * QR_NP;
@@ -213,10 +215,12 @@ __global__ void __launch_bounds__(QRC_THREADS, 1) qr_panel_cluster_kernel(const 
     for (int j = 0; j < jb; ++j) {
         const long long dj = p.j0 + j;
         // ---- CTA-level sums
+        {
+            double v32[32];
 #pragma unroll
-        for (int c = 0; c < QR_NP; ++c) {
-            const double v = warp_sum(part[c]);
-            if (lane == 0) wsum[wid * QR_NP + c] = v;
+            for (int c = 0; c < QR_NP; ++c) v32[c] = part[c];
+            warp_multi_sum<QR_NP>(v32);
+            if (lane < QR_NP) wsum[wid * QR_NP + lane] = v32[0];
         }
         __syncthreads();
         // ---- publish to every CTA of the cluster (DSMEM): thread (dst, c) writes one double
