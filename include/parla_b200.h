@@ -130,6 +130,32 @@ int pla_lsqr_under_long_f64(int64_t len, const double* vt, double* x, double* w,
 int pla_lsqr_ridge_f64(int64_t n, double sd, const double* xw, double* ub, const double* sc_dev, double sa,
                        double su, double* zss, const int* istop_dev, void* stream);
 
+/* ---------------------------------------------------------------- PCG recurrences on device
+ * Replaces parla/comps/determiter/pcg.py:5-47 as called by PcSS1 (parla/comps/determiter/saddle.py:144-160)
+ * on the normal equations (A^T A + delta I) x = A^T b - c.  The Gram product is ONE pla_stream_pass_f64
+ * (flags DOT|AXPY, su = 0): gp = A^T (A p); delta * p is added here.  Single CTA, n-sized vectors;
+ * dstate = PLA_LSQR_NDOUBLE doubles, istate = PLA_LSQR_NINT ints (same buffers/polling as LSQR).
+ *   residual : r = rhs - (gx + delta x)  [gx == NULL: r = rhs], err = |r|; init != 0 also sets the
+ *              stopping threshold tol * err (pcg.py:16,22-23)
+ *   direction: init: delta1 = r.s, p = s (pcg.py:18-20); else beta = r.s / delta1, p = s + beta p, itn += 1
+ *              (pcg.py:39-43); then istop = 0 while (itn < iter_lim && err > threshold) (pcg.py:26), else 1 / 7
+ *   update   : hist[itn] = err; alpha = delta1 / p.(gp + delta p); x += alpha p; unless recompute:
+ *              r -= alpha (gp + delta p), err = |r|   (pcg.py:28-37; recompute on iterations 0, 10, 20, ...)
+ * Every kernel but the init forms is a no-op once istate[PLA_PCG_ISTOP] != 0.                          */
+#define PLA_PCG_RZ 0
+#define PLA_PCG_ERR 1
+#define PLA_PCG_STOP_AT 2
+#define PLA_PCG_ALPHA 3
+#define PLA_PCG_ISTOP 0
+#define PLA_PCG_ITN 1
+#define PLA_PCG_ITERLIM 2
+int pla_pcg_residual_f64(int64_t n, const double* rhs, const double* gx, double delta, const double* x, double* r,
+                         double* dstate, int* istate, int init, double tol, void* stream);
+int pla_pcg_direction_f64(int64_t n, const double* r, const double* s, double* p, double* dstate, int* istate,
+                          int init, int iter_lim, void* stream);
+int pla_pcg_update_f64(int64_t n, const double* gp, double delta, const double* p, double* x, double* r,
+                       double* dstate, const int* istate, double* hist, int recompute, void* stream);
+
 /* ---------------------------------------------------------------- K2: SJLT sketch
  * Replaces `S @ A` for the scipy CSC operator of parla/utils/sketching.py:51-74 applied at
  * parla/drivers/least_squares.py:303,314 (scipy.sparse csc_matvecs).
@@ -159,6 +185,15 @@ int pla_sjlt_plan_status(const void* plan, int64_t* bad_index_count_host);
  * depends only on (seed, col_offset + i), so row-sharded ranks generate consistent slices.         */
 int pla_sjlt_generate(int64_t d, int64_t m, int64_t k, uint64_t seed, int64_t col_offset, int32_t* rows,
                       int8_t* signs, void* stream);
+
+/* Adjoint of the sketching operators on one vector, out[m] = scale * S^T v  (v has d entries):
+ * replaces `S.T @ v[:d]` of parla/drivers/saddlesys.py:291-292 (SPS2 folds c into b).
+ *   pla_sjlt_rmatvec_f64 : S in index form (rows/signs as for pla_sjlt_plan_f64)
+ *   pla_gauss_rmatvec_f64: virtual Gaussian operator G(seed)[0:d, col_offset:col_offset+m]       */
+int pla_sjlt_rmatvec_f64(const int32_t* rows, const int8_t* signs, int64_t m, int64_t k, int64_t d, const double* v,
+                         double scale, double* out, void* stream);
+int pla_gauss_rmatvec_f64(int64_t d, int64_t m, uint64_t seed, int64_t col_offset, double scale, const double* v,
+                          double* out, void* stream);
 
 /* ---------------------------------------------------------------- FP64 tensor-core GEMM (DMMA)
  * C[M x N] = alpha * op(A) * op(B) + beta * C, op(X) = X or X^T (transa/transb = 0/1).

@@ -124,6 +124,81 @@ def spu_case(name, m, n, seed, cond=1e3, sf=4, tol=1e-12, iter_lim=100, rng_seed
                         S_rows=rows.astype(np.int16), S_signs=signs, vec_nnz=k)
 
 
+def saddle_spectrum(kind, n, cond):
+    if kind == 'lin':
+        return np.linspace(cond ** 0.5, cond ** -0.5, num=n)
+    return np.logspace(np.log10(cond) / 2, -np.log10(cond) / 2, num=n)
+
+
+def sps_case(name, alg, m, n, cond, kind, delta, tol, iter_lim, seed=0, rng_seed=1, rhs_scale=1.0, sf=None):
+    """Saddle-point drivers (saddlesys.py): alg in {'sps1', 'sps1_left', 'sps1_right', 'sps2'} on the
+    reference's own test problem (test_saddlesys.py:11-57)."""
+    import types
+    import scipy.linalg as la
+    import parla.drivers.saddlesys as rss
+    import parla.comps.determiter.saddle as rdsad
+    import parla.tests.test_drivers.test_optim.test_saddlesys as rts
+
+    def solve(a, b, sym_pos=False, **kw):                      # scipy >= 1.11 dropped sym_pos
+        return la.solve(a, b, assume_a='pos' if sym_pos else 'gen', **kw)
+    rts.la = types.SimpleNamespace(solve=solve, norm=la.norm, lstsq=la.lstsq, LinAlgError=la.LinAlgError)
+
+    spec = saddle_spectrum(kind, n, cond)
+    ath = rts.make_simple_prob(m, n, spec, delta, np.random.default_rng(seed), rhs_scale=rhs_scale)
+    A, b, c, x_opt, y_opt = orc.saddle_problem(m, n, spec, delta, np.random.default_rng(seed), rhs_scale)
+    assert relerr(A, ath.A) < 1e-13 and relerr(b, ath.b) < 1e-13 and relerr(c, ath.c) < 1e-13
+    # both arms get the SAME inputs: the oracle-built problem (equal to the reference's up to the last bit of
+    # a BLAS nrm2; the digests in the fixture are of these arrays)
+    gauss = alg in ('sps1_left', 'sps1_right')
+    sf = sf if sf is not None else (0.85 if gauss else 3)
+    ref_gen = Tape(rsko.SkOpGA() if gauss else rsko.SkOpSJ())
+    orc_gen = Tape(orc.SkOpGA() if gauss else orc.SkOpSJ())
+    if alg == 'sps2':
+        ref_alg, orc_alg = rss.SPS2(ref_gen, sf, rdsad.PcSS2()), orc.SPS2(orc_gen, sf)
+    else:
+        ref_alg, orc_alg = rss.SPS1(ref_gen, sf, rdsad.PcSS1()), orc.SPS1(orc_gen, sf)
+        if gauss:
+            ref_alg.nystrom_strategy = orc_alg.nystrom_strategy = alg.split('_')[1]
+    x_ref, y_ref, log_ref = ref_alg(A.copy(), b.copy(), c.copy(), delta, tol, iter_lim,
+                                    np.random.default_rng(rng_seed), logging=True)
+    x_orc, y_orc, log_orc = orc_alg(A.copy(), b.copy(), c.copy(), delta, tol, iter_lim,
+                                    np.random.default_rng(rng_seed), logging=True)
+    S_ref, S_orc = ref_gen.ops[0], orc_gen.ops[0]
+    same_S = bool(np.array_equal(S_ref, S_orc)) if gauss else (S_ref != S_orc).nnz == 0
+    e_x, e_y = relerr(x_orc, x_ref), relerr(y_orc, y_ref)
+    its = (log_ref.errors.size - 1, log_orc.errors.size - 1)
+    e_opt = relerr(x_ref, x_opt)
+    print(f"{name:34s} iters ref/orc {its}  |dx|/|x| {e_x:.2e} |dy|/|y| {e_y:.2e}  ref vs x_opt {e_opt:.1e}  "
+          f"S identical {same_S}")
+    assert same_S and abs(its[0] - its[1]) <= 1 and e_x < 1e-8 and e_y < 1e-8, (e_x, e_y, its)
+    fx = dict(alg=alg, m=m, n=n, cond=cond, kind=kind, delta=delta, tol=tol, iter_lim=iter_lim, seed=seed,
+              rng_seed=rng_seed, rhs_scale=rhs_scale, sf=sf, x=x_ref, y_norm=np.linalg.norm(y_ref),
+              y_probe=y_ref[::max(1, m // 64)], errors=log_ref.errors, x_opt=x_opt,
+              A_sha=digest(A), b_sha=digest(b), c_sha=digest(c))
+    if gauss:
+        fx.update(S_sha=digest(S_ref))
+    else:
+        rows, signs, k = orc.sjlt_index_form(S_ref)
+        fx.update(S_rows=rows.astype(np.int16), S_signs=signs, vec_nnz=k)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+
+
+def sps_cases():
+    sps_case("sps1_lin_1000x100", 'sps1', 1000, 100, 1e5, 'lin', 0.0, 1e-6 / 5e3, 50)
+    sps_case("sps1_lin_ridge_1000x100", 'sps1', 1000, 100, 1e5, 'lin', 0.5, 1e-6 / 5e3, 50)
+    sps_case("sps1_log_ridge_1000x100", 'sps1', 1000, 100, 1e5, 'log', 0.5, 1e-6 / 5e3, 50, rng_seed=4)
+    sps_case("sps1_hiacc_500x50", 'sps1', 500, 50, 1e3, 'lin', 1.0, 1e-12, 50, rng_seed=15)
+    sps_case("sps1_tiny_500x50", 'sps1', 500, 50, 1e8, 'lin', 0.0, 1e-8, 50, rhs_scale=1e-9, rng_seed=31)
+    sps_case("sps1_nysleft_1000x100", 'sps1_left', 1000, 100, 1e5, 'lin', 0.0, 1e-10, 100)
+    sps_case("sps1_nysleft_ridge_1000x100", 'sps1_left', 1000, 100, 1e5, 'log', 0.3, 1e-10, 100, rng_seed=42)
+    sps_case("sps1_nysright_1000x100", 'sps1_right', 1000, 100, 1e5, 'lin', 0.0, 1e-10, 100)
+    sps_case("sps1_nysright_ridge_1000x100", 'sps1_right', 1000, 100, 1e5, 'log', 0.3, 1e-10, 100, rng_seed=4)
+    sps_case("sps2_lin_1000x100", 'sps2', 1000, 100, 1e5, 'lin', 0.0, 1e-12, 50)
+    sps_case("sps2_lin_ridge_1000x100", 'sps2', 1000, 100, 1e5, 'lin', 0.5, 1e-12, 50)
+    sps_case("sps2_log_ridge_1000x100", 'sps2', 1000, 100, 1e5, 'log', 0.5, 1e-12, 50, rng_seed=15)
+    sps_case("sps2_hiacc_500x50", 'sps2', 500, 50, 1e3, 'lin', 1.0, 1e-12, 50, rng_seed=42)
+
+
 def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pass=2, evd=False):
     rng = np.random.default_rng(seed)
     if evd:
@@ -189,6 +264,9 @@ def philox_case():
 
 
 if __name__ == "__main__":
+    if "--only-sps" in sys.argv:
+        sps_cases()
+        sys.exit(0)
     if "--only-spu" in sys.argv:
         spu_case("spu1_sjlt_800x50", 800, 50, 31)
         spu_case("spu1_sjlt_2000x96", 2000, 96, 32, cond=1e5)
@@ -213,4 +291,5 @@ if __name__ == "__main__":
     lowrank_case("evd1_qb1_120", 120, 120, 12, 12, 25, evd=True)
     spu_case("spu1_sjlt_800x50", 800, 50, 31)
     spu_case("spu1_sjlt_2000x96", 2000, 96, 32, cond=1e5)
+    sps_cases()
     print("golden fixtures written to", OUT)

@@ -487,6 +487,213 @@ class SPO:
         return x, log
 
 
+# ------------------------------------------------------------------------------------------
+#  Saddle-point systems            (reference: comps/determiter/pcg.py, comps/determiter/saddle.py:88-176,
+#                                   drivers/saddlesys.py:89-327)
+# ------------------------------------------------------------------------------------------
+
+def pcg(mv_mat, rhs, mv_pre, iter_lim, tol, x0):
+    """Preconditioned conjugate gradients, pcg.py:5-47.
+
+    History entry i is ||rhs - mat x_i||_2 at the START of iteration i (:28); the residual is
+    recomputed from x on iterations 0, 10, 20, ... (:34-35) and updated recursively otherwise
+    (:37); the loop runs while ||r|| > tol * ||r_0|| (:23,:26).  Returns (x, history[:iters]).
+    """
+    x = np.array(x0, dtype=np.float64, copy=True)
+    r = rhs - mv_mat(x)
+    p = mv_pre(r)
+    rz = float(r @ p)
+    err = float(np.linalg.norm(r))
+    stop_at = tol * err
+    hist = []
+    it = 0
+    while it < iter_lim and err > stop_at:
+        hist.append(err)
+        q = mv_mat(p)
+        step = rz / float(p @ q)
+        x = x + step * p
+        r = rhs - mv_mat(x) if it % 10 == 0 else r - step * q
+        err = float(np.linalg.norm(r))
+        s = mv_pre(r)
+        rz_prev, rz = rz, float(r @ s)
+        p = s + (rz / rz_prev) * p
+        it += 1
+    return x, np.array(hist, dtype=np.float64)
+
+
+def pcss1(A, b, c, delta, tol, iter_lim, R, upper_tri, z0):
+    """PcSS1.__call__, saddle.py:96-176: PCG on (A'A + delta I) x = A'b - c with the
+    preconditioner R R' (full rank) or R~ R~' + (I - V V') (low rank, :121-131,:134-142).
+    Returns (x, y = b - A x, history).  R is not modified (the reference rescales it in place)."""
+    m, n = A.shape
+    if b is None:
+        b = np.zeros(m)
+    if b.ndim != 1:
+        raise NotImplementedError()
+    if upper_tri:
+        raise NotImplementedError()                             # :117-118
+    full = R.shape[1] == n
+    if full:
+        Rs, V = R, None
+    else:
+        sv = 1.0 / np.linalg.norm(R, axis=0)                    # :124
+        V = R * sv
+        sv = np.sqrt(sv ** 2 + delta)                           # :127-129
+        Rs = V / (sv / sv[-1])                                  # :130-131
+
+    def mv_pre(vec):                                            # :134-142
+        out = Rs @ (Rs.T @ vec)
+        if not full:
+            out = out + vec - V @ (V.T @ vec)
+        return out
+
+    def mv_gram(vec):                                           # :144-148
+        return A.T @ (A @ vec) + delta * vec
+
+    rhs = A.T @ b
+    if c is not None:
+        rhs = rhs - c
+    x0 = np.zeros(n) if (z0 is None or not full) else Rs @ z0   # :154-158
+    x, hist = pcg(mv_gram, rhs, mv_pre, iter_lim, tol, x0)
+    return x, b - A @ x, hist
+
+
+class SPS1:
+    """SVD / Nystrom sketch-and-precondition for saddle systems with PCG, saddlesys.py:89-223."""
+
+    def __init__(self, sketch_op_gen, sampling_factor, iterative_solver=None):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+        self.iterative_solver = iterative_solver if iterative_solver is not None else pcss1
+        self.nystrom_strategy = 'left'
+
+    def __call__(self, A, b, c, delta, tol, iter_lim, rng, logging=True):
+        m, n = A.shape
+        d = int(self.sampling_factor * n)                       # :134 (no dim_checks here)
+        rng = np.random.default_rng(rng)
+        assert self.nystrom_strategy in ('left', 'right')
+        if b is None:
+            b = np.zeros(m)
+        clock = time.time if logging else (lambda: 0.0)
+        log = SketchAndPrecondLog()
+        if d >= n:                                              # :146-157
+            t = clock()
+            S = self.sketch_op_gen(d, m, rng)
+            A_ske = S @ A
+            if delta > 0:
+                A_ske = np.vstack((A_ske, math.sqrt(delta) * np.eye(n)))
+            log.time_sketch = clock() - t
+            t = clock()
+            M, _U, sigma, Vh = svd_right_precond(A_ske)
+            log.time_factor = clock() - t
+        elif self.nystrom_strategy == 'right':                  # :159-170
+            t = clock()
+            S = self.sketch_op_gen(n, d, rng)
+            Y = A @ S
+            log.time_sketch = clock() - t
+            t = clock()
+            Q = orth(Y)
+            _U, sigma, Vh = sla.svd(Q.T @ A, full_matrices=False)
+            M = Vh.T / sigma
+            log.time_factor = clock() - t
+        else:                                                   # :171-184
+            t = clock()
+            S = self.sketch_op_gen(d, m, rng)
+            A_ske = S @ A
+            log.time_sketch = clock() - t
+            t = clock()
+            V = orth(A_ske.T)
+            _U, sigma, Wt = sla.svd(A @ V, full_matrices=False)
+            M = V @ (Wt.T / sigma)
+            log.time_factor = clock() - t
+
+        rhs = A.T @ b
+        if c is not None:
+            rhs = rhs - c
+        t = clock()
+        z_ske = None
+        if d >= n:                                              # :198-204
+            z_ske = (Vh @ rhs) / sigma
+            x_ske = M @ z_ske
+            rhs_pc = M.T @ rhs
+            lhs_pc = M.T @ (A.T @ (A @ x_ske) + delta * x_ske)
+            if np.linalg.norm(lhs_pc - rhs_pc) >= np.linalg.norm(rhs_pc):
+                z_ske = None
+        log.time_presolve = clock() - t
+
+        t = clock()
+        x, y, hist = self.iterative_solver(A, b, c, delta, tol, iter_lim, M, False, z_ske)   # :212
+        log.time_iterate = clock() - t
+        if logging:
+            log.wrap_up(hist, float(np.linalg.norm(rhs)))       # :219
+        return x, y, log
+
+
+class SPS2:
+    """Sketch, reduce the saddle system to over-determined least squares, precondition, LSQR.
+    saddlesys.py:226-327."""
+
+    def __init__(self, sketch_op_gen, sampling_factor, iterative_solver=None):
+        self.sketch_op_gen = sketch_op_gen
+        self.sampling_factor = sampling_factor
+        self.iterative_solver = iterative_solver
+
+    def __call__(self, A, b, c, delta, tol, iter_lim, rng, logging=False):
+        m, n = A.shape
+        sd = math.sqrt(delta)
+        d = dim_checks(self.sampling_factor, m, n)
+        rng = np.random.default_rng(rng)
+        if b is None:
+            b = np.zeros(m)
+        clock = time.time if logging else (lambda: 0.0)
+        log = SketchAndPrecondLog()
+
+        t = clock()                                             # :275-279
+        S = self.sketch_op_gen(d, m, rng)
+        A_ske = S @ A
+        if delta > 0:
+            A_ske = np.vstack((A_ske, sd * np.eye(n)))
+        log.time_sketch = clock() - t
+
+        t = clock()                                             # :282-284
+        M, U, sigma, Vh = svd_right_precond(A_ske)
+        log.time_factor = clock() - t
+
+        t = clock()                                             # :287-295
+        A_aug = np.vstack((A, sd * np.eye(n))) if delta > 0 else A
+        b_aug = np.concatenate((b, np.zeros(n))) if delta > 0 else b.copy()
+        if c is not None and np.linalg.norm(c) > 0:
+            v = U @ ((Vh @ c) / sigma)
+            b_aug[:m] -= S.T @ v[:d]
+            if delta > 0:
+                b_aug[m:] -= v[d:]
+        log.time_convert = clock() - t
+
+        t = clock()                                             # :298-304
+        z_ske = U[:d].T @ (S @ b_aug[:m])
+        if delta > 0:
+            z_ske = z_ske + U[d:].T @ b_aug[m:]
+        x_ske = M @ z_ske
+        if np.linalg.norm(b_aug - A_aug @ x_ske) >= np.linalg.norm(b_aug):
+            z_ske = None
+        log.time_presolve = clock() - t
+
+        t = clock()                                             # :307-313
+        solver = self.iterative_solver if self.iterative_solver is not None else pcss2_overdetermined_full
+        x, _y_aug, hist = solver(A_aug, b_aug, None, 0.0, tol, iter_lim, M, False, z_ske)
+        log.time_iterate = clock() - t
+        y = b - A @ x
+        if logging:                                             # :316-321
+            log.wrap_up(hist, float(np.linalg.norm(M.T @ (A_aug.T @ b_aug))))
+        return x, y, log
+
+
+def pcss2_overdetermined_full(A, b, c, delta, tol, iter_lim, R, upper_tri, z0):
+    """PcSS2 with the PrecondSaddleSolver signature (saddle.py:187), over-determined branch only."""
+    assert c is None or np.linalg.norm(c) == 0
+    return pcss2_overdetermined(A, b, delta, tol, iter_lim, R, upper_tri, z0)
+
+
 class SSO1:
     """Sketch-and-solve, least_squares.py:114-189."""
 
@@ -703,3 +910,33 @@ def exponent_spectrum(n_rows, n_cols, rank, rng, spectrum_param, factors=False):
     """tests/matmakers.py:34-36."""
     spec = np.exp((-np.arange(1, rank) + 1) / spectrum_param)
     return rand_low_rank(n_rows, n_cols, spec, rng, factors)
+
+
+def saddle_problem(m, n, spectrum, delta, rng, rhs_scale=1.0):
+    """Test problem of tests/test_drivers/test_optim/test_saddlesys.py:11-57 (make_simple_prob):
+    A = U diag(spectrum) Vt, b with 70 % of its mass in range(A), Gaussian c; returns
+    (A, b, c, x_opt, y_opt) with (A'A + delta I) x_opt = A'b - c and y_opt = b - A x_opt."""
+    rng = np.random.default_rng(rng)
+    rank = spectrum.size
+    U = orthonormal_operator(m, rank, rng)
+    Vt = orthonormal_operator(rank, n, rng)
+    A = (U * spectrum) @ Vt
+    b0 = rng.standard_normal(m)
+    b_in = U @ (U.T @ b0)
+    b_out = b0 - b_in
+    b_in *= np.mean(spectrum) / np.linalg.norm(b_in)
+    b_out *= np.mean(spectrum) / np.linalg.norm(b_out)
+    b = 0.7 * b_in + (1 - 0.7) * b_out
+    c = rng.standard_normal(n)
+    gram = A.T @ A + delta * np.eye(n)
+    rhs = A.T @ b - c
+    if rhs_scale != 1.0:
+        scale = rhs_scale / np.linalg.norm(rhs)
+        rhs *= scale
+        b *= scale
+        c *= scale
+    try:
+        x_opt = sla.solve(gram, rhs, assume_a='pos')
+    except sla.LinAlgError:
+        x_opt = sla.lstsq(gram, rhs)[0]
+    return A, b, c, x_opt, b - A @ x_opt

@@ -11,8 +11,10 @@ from .comps.sketchers.aware import RS1, RowSketcher
 from .comps.qb import QB1, QB2, QBDecomposer
 from .comps.rangefinders import RF1, RangeFinder
 from .comps.determiter.logging import SketchAndPrecondLog
-from .comps.determiter.saddle import PcSS2, PrecondSaddleSolver
+from .comps.determiter.saddle import PcSS1, PcSS2, PrecondSaddleSolver, pcss1, pcss2
+from .comps.determiter.pcg import pcg
 from .drivers.least_squares import SPO, SSO1, OverLstsqSolver, SPU1, UnderLstsqSolver
+from .drivers.saddlesys import SPS1, SPS2, SaddleSolver, sps
 from .drivers.svd import SVD1, SVDecomposer
 from .drivers.evd import EVD1, EVDecomposer
 from .parallel import RowSharded

@@ -33,6 +33,11 @@ SIGNATURES = {
     "pla_lsqr_under_head_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pla_lsqr_under_tail_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pla_lsqr_under_long_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_sz, c_vp]),
+    "pla_pcg_residual_f64": (c_int, [c_i64, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_vp]),
+    "pla_pcg_direction_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "pla_pcg_update_f64": (c_int, [c_i64, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "pla_sjlt_rmatvec_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_dbl, c_vp, c_vp]),
+    "pla_gauss_rmatvec_f64": (c_int, [c_i64, c_i64, c_u64, c_i64, c_dbl, c_vp, c_vp, c_vp]),
     "pla_sjlt_plan_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pla_sjlt_plan_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pla_sjlt_plan_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),

@@ -29,9 +29,11 @@ def _poll_buffers():
 
 
 def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=False, calc_var=False,
-         x0=None, _warm=None):
+         x0=None, _warm=None, _b_ridge=None):
     """A: PrecondOperator; b: device vector (this rank's rows).  Returns the reference's 10-tuple
-    (x, istop, itn, r1norm, r2norm, anorm, acond, arnorms, xnorm, var); x is a device tensor."""
+    (x, istop, itn, r1norm, r2norm, anorm, acond, arnorms, xnorm, var); x is a device tensor.
+    ``_b_ridge`` (n-vector, only with delta > 0) is the part of the right-hand side that sits on the
+    implicit ridge rows ``sqrt(delta) I`` (zero in SPO; SPS2 puts ``-v[d:]`` there, saddlesys.py:293-294)."""
     if damp != 0.0 or calc_var:
         raise NotImplementedError("PARLA always calls lsqr with damp=0, calc_var=False")
     n = A.shape[1]
@@ -47,16 +49,20 @@ def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=F
     istate = torch.zeros(K.LSQR_NINT, dtype=torch.int32, device=dev)
     hist = torch.full((iter_lim,), -1.0, dtype=F64, device=dev)
     bsq = allreduce_(K.sumsq(b), A.group)
+    if _b_ridge is not None:
+        bsq = bsq + K.sumsq(_b_ridge)
 
     if _warm is not None:                       # presolve already did  u = b - A_pc x0  (lsqr.py:367-370)
         u, ub, zss = _warm["u"], _warm["ub"], _warm["zss"]
         t.copy_(_warm["t"])
     else:
         u = b.clone()
-        ub = torch.zeros(A.n, dtype=F64, device=dev) if A.delta > 0 else None
+        ub = None
+        if A.delta > 0:
+            ub = torch.zeros(A.n, dtype=F64, device=dev) if _b_ridge is None else _b_ridge.clone()
         zss = torch.empty(A.n + 1, dtype=F64, device=dev)
         if x0 is None:
-            A.adjoint_pass(u, None, zss, t)     # u = b, beta = |b|, A^T b   (:363-366,:372-375)
+            A.adjoint_pass(u, None if _b_ridge is None else ub, zss, t)     # u = b, beta = |b|, A^T b   (:363-366,:372-375)
             A.atb = zss[:A.n].clone()
         else:
             A.bidiag_pass(x0, u, ub, zss, xw, t, sa=-1.0, su=1.0)

@@ -210,6 +210,28 @@ def lsqr_under_long(vt, x, w, dstate, istate, itn, add_to_ww=False):
                                                    ws.data_ptr(), ws.numel(), _stream()), "pla_lsqr_under_long_f64")
 
 
+# ---------------------------------------------------------------------------------------- PCG state
+PCG_ERR = 1             # dstate slot of |r| (see include/parla_b200.h)
+
+
+def pcg_residual(rhs, gx, delta, x, r, dstate, istate, init=False, tol=0.0):
+    _lib.check(_lib.load().pla_pcg_residual_f64(rhs.numel(), rhs.data_ptr(), _p(gx), float(delta), _p(x), r.data_ptr(),
+                                                dstate.data_ptr(), istate.data_ptr(), 1 if init else 0, float(tol),
+                                                _stream()), "pla_pcg_residual_f64")
+
+
+def pcg_direction(r, s, p, dstate, istate, init=False, iter_lim=0):
+    _lib.check(_lib.load().pla_pcg_direction_f64(r.numel(), r.data_ptr(), s.data_ptr(), p.data_ptr(), dstate.data_ptr(),
+                                                 istate.data_ptr(), 1 if init else 0, int(iter_lim), _stream()),
+               "pla_pcg_direction_f64")
+
+
+def pcg_update(gp, delta, p, x, r, dstate, istate, hist, recompute):
+    _lib.check(_lib.load().pla_pcg_update_f64(p.numel(), gp.data_ptr(), float(delta), p.data_ptr(), x.data_ptr(),
+                                              r.data_ptr(), dstate.data_ptr(), istate.data_ptr(), hist.data_ptr(),
+                                              1 if recompute else 0, _stream()), "pla_pcg_update_f64")
+
+
 def sumsq(x, out=None):
     lib = _lib.load()
     x = _vec(x, "x")
@@ -305,6 +327,34 @@ class SjltPlan:
                                     1 if accumulate else 0, _p(ws), ws.numel() if ws is not None else 0, _stream())
         _lib.check(rc, "pla_sjlt_apply_f64")
         return out
+
+
+def sjlt_rmatvec(rows, signs, d, v, scale, out=None):
+    """out = scale * S^T v for the SJLT in index form (rows/signs [m, k])."""
+    _req(rows, "rows", torch.int32)
+    _req(signs, "signs", torch.int8)
+    rows, signs = rows.contiguous(), signs.contiguous()
+    v = _vec(v, "v")
+    if v.numel() != d:
+        raise ValueError(f"S^T v: v has {v.numel()} entries, the operator has {d} rows")
+    m, k = rows.shape
+    if out is None:
+        out = torch.empty(m, dtype=F64, device=v.device)
+    _lib.check(_lib.load().pla_sjlt_rmatvec_f64(rows.data_ptr(), signs.data_ptr(), m, k, int(d), v.data_ptr(),
+                                                float(scale), out.data_ptr(), _stream()), "pla_sjlt_rmatvec_f64")
+    return out
+
+
+def gauss_rmatvec(d, m, seed, scale, v, col_offset=0, out=None):
+    """out = scale * G(seed)[0:d, col_offset:col_offset+m]^T v  (virtual Gaussian operator)."""
+    v = _vec(v, "v")
+    if v.numel() != d:
+        raise ValueError(f"S^T v: v has {v.numel()} entries, the operator has {d} rows")
+    if out is None:
+        out = torch.empty(m, dtype=F64, device=v.device)
+    _lib.check(_lib.load().pla_gauss_rmatvec_f64(int(d), int(m), ctypes.c_uint64(seed), int(col_offset), float(scale),
+                                                 v.data_ptr(), out.data_ptr(), _stream()), "pla_gauss_rmatvec_f64")
+    return out
 
 
 def sjlt_generate(d, m, k, seed, col_offset=0, device="cuda"):

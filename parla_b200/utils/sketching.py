@@ -75,6 +75,11 @@ class SketchOperator:
         """Operator restricted to columns [first, first+count) (a row shard of A)."""
         raise NotImplementedError()
 
+    def rmatvec(self, v, m_local=None, row_offset=0):
+        """S[:, off:off+m_local]^T @ v for ONE vector v (d entries) -> m_local entries
+        (``S.T @ v[:d]``, saddlesys.py:291)."""
+        raise NotImplementedError()
+
     @property
     def T(self):
         return self.to_dense().T
@@ -102,6 +107,10 @@ class GaussianOperator(SketchOperator):
 
     def to_dense(self):
         return K.philox_normal_fill(self.shape[0], self.shape[1], self.seed, self.scale, device=self.device)
+
+    def rmatvec(self, v, m_local=None, row_offset=0):
+        m_local = self.shape[1] if m_local is None else m_local
+        return K.gauss_rmatvec(self.shape[0], m_local, self.seed, self.scale, v, col_offset=row_offset)
 
     def column_slice(self, first, count):
         return self            # virtual: the column offset is passed to the kernel (sketch_into)
@@ -131,6 +140,9 @@ class SJLTOperator(SketchOperator):
     def column_slice(self, first, count):
         return SJLTOperator(self.shape[0], self.rows[first:first + count].contiguous(),
                             self.signs[first:first + count].contiguous())
+
+    def rmatvec(self, v, m_local=None, row_offset=0):
+        return K.sjlt_rmatvec(self.rows, self.signs, self.shape[0], v, self.scale)
 
     def to_dense(self):
         d, m = self.shape
@@ -163,6 +175,9 @@ class DenseOperator(SketchOperator):
 
     def column_slice(self, first, count):
         return DenseOperator(self.S[:, first:first + count])
+
+    def rmatvec(self, v, m_local=None, row_offset=0):
+        return K.rmatvec(self.S, v)[:self.shape[1]].clone()
 
 
 def as_device_operator(S, device=None):

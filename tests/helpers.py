@@ -57,6 +57,71 @@ SPU_FIXTURES = ["spu1_sjlt_800x50", "spu1_sjlt_2000x96"]
 LOWRANK_FIXTURES = ["svd1_qb1_200x50", "svd1_qb2_200x50", "svd1_qb2_tol_200x50", "svd1_qb1_over_50x200", "evd1_qb1_120"]
 
 
+SPS_FIXTURES = ["sps1_lin_1000x100", "sps1_lin_ridge_1000x100", "sps1_log_ridge_1000x100", "sps1_hiacc_500x50",
+                "sps1_tiny_500x50", "sps1_nysleft_1000x100", "sps1_nysleft_ridge_1000x100", "sps1_nysright_1000x100",
+                "sps1_nysright_ridge_1000x100", "sps2_lin_1000x100", "sps2_lin_ridge_1000x100",
+                "sps2_log_ridge_1000x100", "sps2_hiacc_500x50"]
+
+
+# PCG with a LOW-RANK (Nystrom) preconditioner and delta = 0 is not a contraction: the residual norm climbs
+# back to ~0.5 |r0| mid-run and rounding differences grow ~10x per iteration.  The reference run against
+# ITSELF with OPENBLAS_NUM_THREADS=1 vs 8 (measured in the build container, oracle == reference bit for bit)
+# gives 77 vs 83 and 59 vs 51 iterations for these two fixtures, histories equal to 1e-6 only up to iteration
+# 19 / 15, and x equal to 6e-12.  Parity for them is therefore: history prefix, iteration count within 20 %, x.
+SPS_CHAOTIC = {"sps1_nysleft_1000x100": 12, "sps1_nysright_1000x100": 10}
+
+
+def assert_history_close(h, h_ref, rtol=1e-6, chaotic_prefix=None, atol_rel=1e-9):
+    """Iteration count and logged error history of an iterative solver against the reference's."""
+    if chaotic_prefix is None:
+        assert abs(h.size - h_ref.size) <= 1, (h.size, h_ref.size)
+        k = min(h.size, h_ref.size)
+        assert np.allclose(h[:k], h_ref[:k], rtol=rtol, atol=atol_rel * h_ref[0]), np.max(np.abs(h[:k] / h_ref[:k] - 1))
+    else:
+        assert abs(h.size - h_ref.size) <= 0.2 * h_ref.size, (h.size, h_ref.size)
+        k = chaotic_prefix
+        assert np.allclose(h[:k], h_ref[:k], rtol=rtol, atol=0), np.max(np.abs(h[:k] / h_ref[:k] - 1))
+
+
+def saddle_problem_from_fixture(fx):
+    """(A, b, c, x_opt) of the reference's saddle-system test problem (test_saddlesys.py:11-57)."""
+    from oracle import parla_oracle as orc
+    n, cond = int(fx["n"]), float(fx["cond"])
+    if str(fx["kind"]) == "lin":
+        spec = np.linspace(cond ** 0.5, cond ** -0.5, num=n)
+    else:
+        spec = np.logspace(np.log10(cond) / 2, -np.log10(cond) / 2, num=n)
+    A, b, c, x_opt, _ = orc.saddle_problem(int(fx["m"]), n, spec, float(fx["delta"]),
+                                           np.random.default_rng(int(fx["seed"])), float(fx["rhs_scale"]))
+    assert digest(A) == str(fx["A_sha"]) and digest(b) == str(fx["b_sha"]) and digest(c) == str(fx["c_sha"]), \
+        "numpy's RNG stream / LAPACK QR differs from the one the fixture was generated with"
+    return A, b, c, x_opt
+
+
+def sps_operator_from_fixture(fx):
+    """The reference's sketching operator of a saddle fixture (SJLT stored; Gaussian regenerated + hash-checked)."""
+    from oracle import parla_oracle as orc
+    alg, m, n = str(fx["alg"]), int(fx["m"]), int(fx["n"])
+    d = int(float(fx["sf"]) * n)
+    if "S_rows" in fx:
+        return sjlt_from_fixture(fx, d, m)
+    shape = (n, d) if alg == "sps1_right" else (d, m)
+    S = orc.gaussian_operator(shape[0], shape[1], np.random.default_rng(int(fx["rng_seed"])))
+    assert digest(S) == str(fx["S_sha"]), "regenerated Gaussian operator differs from the fixture's"
+    return S
+
+
+def sps_algorithm(mod, fx, gen):
+    """SPS1 / SPS2 of module ``mod`` (the oracle or parla_b200) configured as the fixture's case."""
+    alg = str(fx["alg"])
+    if alg == "sps2":
+        return mod.SPS2(gen, float(fx["sf"]))
+    a = mod.SPS1(gen, float(fx["sf"]))
+    if alg in ("sps1_left", "sps1_right"):
+        a.nystrom_strategy = alg.split("_")[1]
+    return a
+
+
 class Replay:
     """sketch_op_gen that hands back a prerecorded operator (reference S replayed on the GPU path)."""
 
