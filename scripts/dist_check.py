@@ -49,6 +49,28 @@ def main():
     xs, _ = rla.SPO(lambda d, mm, r: S, 4, 'qr')(Ash, bsh, 0.0, 1e-12, 100, None)
     report("SPO[replayed scipy SJLT] sharded vs oracle", float(np.linalg.norm(xs.cpu().numpy() - x_ref) / np.linalg.norm(x_ref)), 1e-10)
 
+    # ---------------- saddle-point systems (SPS2: LSQR; SPS1: PCG with SVD and Nystrom preconditioners)
+    c = rng.standard_normal(n)
+    cd = torch.from_numpy(c).to(dev)
+    for name, mk, tol in (("SPS2[SkOpSJ]", lambda: rla.SPS2(rla.SkOpSJ(8), 4), 1e-12),
+                          ("SPS2[SkOpGA]", lambda: rla.SPS2(rla.SkOpGA(), 4), 1e-12),
+                          ("SPS1[SkOpSJ]", lambda: rla.SPS1(rla.SkOpSJ(8), 3), 1e-13)):
+        x1, y1, log1 = mk()(Ad, bd, cd, 0.4, tol, 100, 9, logging=True)
+        xs, ys, logs = mk()(Ash, bsh, cd, 0.4, tol, 100, 9, logging=True)
+        report(f"{name} x sharded vs 1 GPU, {logs.iters}/{log1.iters} its",
+               float(torch.linalg.vector_norm(xs - x1) / torch.linalg.vector_norm(x1)), 1e-10)
+        report(f"{name} y (local rows) sharded vs 1 GPU",
+               float(torch.linalg.vector_norm(ys - y1[mine]) / torch.linalg.vector_norm(y1)), 1e-10)
+    for strat in ("left", "right"):
+        def mk():
+            a = rla.SPS1(orc.SkOpGA(), 0.85)
+            a.nystrom_strategy = strat
+            return a
+        x1, y1, log1 = mk()(Ad, bd, cd, 0.4, 1e-13, 400, 9, logging=True)
+        xs, ys, logs = mk()(Ash, bsh, cd, 0.4, 1e-13, 400, 9, logging=True)
+        report(f"SPS1[Nystrom {strat}] x sharded vs 1 GPU, {logs.iters}/{log1.iters} its",
+               float(torch.linalg.vector_norm(xs - x1) / torch.linalg.vector_norm(x1)), 1e-9)
+
     # ---------------- low rank: SVD1 over QB1 / QB2, numpy test matrices replayed (identical on both paths)
     A2 = orc.exponent_spectrum(2048 * world, 300, 120, np.random.default_rng(1), 8.0)
     A2d = torch.from_numpy(A2).to(dev)

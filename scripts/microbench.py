@@ -137,6 +137,25 @@ def main():
                               "iters": log.iters, "passes": log.passes_over_A,
                               "ms_per_iter": round(1e3 * log.time_iterate / max(log.iters, 1), 3),
                               "err_last": float(log.errors[-1])}), flush=True)
+    if want("sps"):
+        # saddle-point system at the headline size: SPS2 (LSQR) and SPS1 (PCG; one fused Gram pass per iteration)
+        x0 = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+        b, _ = K.matvec(A, x0)
+        b += 0.1 * torch.randn(m, dtype=torch.float64, device="cuda", generator=g)
+        c = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+        delta = 0.5
+        for name, alg, tol in (("SPS2-lsqr", rla.SPS2(rla.SkOpSJ(8), 4), 1e-12), ("SPS1-pcg", rla.SPS1(rla.SkOpSJ(8), 4), 1e-12)):
+            for rep in range(2):
+                x, y, log = alg(A, b, c, delta, tol, 100, 3, logging=True)
+            g1 = K.rmatvec(A, y)[:n] - delta * x - c                 # A'y - delta x - c  (second block row)
+            tot = log.time_sketch + log.time_factor + log.time_convert + log.time_presolve + log.time_iterate
+            print(json.dumps({"solve": name, "m": m, "n": n, "delta": delta, "total_s": round(tot, 4),
+                              "sketch": round(log.time_sketch, 4), "factor": round(log.time_factor, 4),
+                              "convert": round(log.time_convert, 4), "presolve": round(log.time_presolve, 4),
+                              "iterate": round(log.time_iterate, 4), "iters": log.iters,
+                              "ms_per_iter": round(1e3 * log.time_iterate / max(log.iters, 1), 3),
+                              "block2_resid_rel": float(torch.linalg.vector_norm(g1) / torch.linalg.vector_norm(c)),
+                              "err_first_last": [float(log.errors[0]), float(log.errors[-1])]}), flush=True)
 
 
 if __name__ == "__main__":
