@@ -38,5 +38,15 @@ for gen in (rla.SkOpSJ(8), rla.SkOpGA()):
         assert np.linalg.norm(x.cpu().numpy() - ref) < 1e-9 * np.linalg.norm(ref)
 y, _ = rla.SPU1(rla.SkOpSJ(8), 4)(dev(A), dev(rng.standard_normal(30)), 1e-12, 60, 1)
 U, s, Vh = rla.SVD1(rla.QB2(rla.RF1(rla.RS1(rla.SkOpGA(), 2, rla.orth, 1)), 8, False))(dev(A), 16, 0.0, 0, 1)
+c = rng.standard_normal(30)
+G = A.T @ A + 0.2 * np.eye(30)
+for gen in (rla.SkOpSJ(8), rla.SkOpGA()):
+    for alg in (rla.SPS2(gen, 4), rla.SPS1(gen, 4)):
+        x, yv, log = alg(dev(A), dev(b), dev(c), 0.2, 1e-12, 60, 1, logging=True)
+        ref = np.linalg.solve(G, A.T @ b - c)
+        assert np.linalg.norm(x.cpu().numpy() - ref) < 1e-8 * np.linalg.norm(ref)
+nys = rla.SPS1(rla.SkOpGA(), 0.8)
+x, yv, log = nys(dev(A), dev(b), dev(c), 0.2, 1e-12, 60, 1, logging=True)
+assert np.linalg.norm(x.cpu().numpy() - ref) < 1e-8 * np.linalg.norm(ref)
 torch.cuda.synchronize()
 print("sanitize_smoke OK")
