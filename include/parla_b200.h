@@ -195,6 +195,19 @@ int pla_sjlt_rmatvec_f64(const int32_t* rows, const int8_t* signs, int64_t m, in
 int pla_gauss_rmatvec_f64(int64_t d, int64_t m, uint64_t seed, int64_t col_offset, double scale, const double* v,
                           double* out, void* stream);
 
+/* ---------------------------------------------------------------- SRCT sketch (subsampled cosine transform)
+ * Replaces `apply_srct` (parla/utils/sketching.py:118-176: mat[perm] * e -> scipy.fft.dct(axis=0, 'ortho') -> rows r)
+ * as used by `srct_operator` / `SkOpTC` (:179-201, comps/sketchers/oblivious.py:68-72).  Only the d sampled rows
+ * are computed: a pruned two-level DCT whose two levels are pla_gemm_f64 calls (see csrc/srct.cu).
+ *   pla_srct_weights_f64: out[i, c] = f(k_i) cos(pi (2j+1) k_i / 2m) e[j],  j = jmap ? jmap[j0+c] : j0+c,
+ *       and with_sin: out[i, ncols+c] = -sgn_i f(k_i) sin(...) e[j];  f = sqrt(1/m) (k = 0) or sqrt(2/m)
+ *       (jmap/e/sgn may be NULL).  Angles reduced exactly in 64-bit integers.
+ *   pla_gather_rows_scale_f64: out[t, c] = e[t] * A[perm[t], c0+c]   (`mat[perm, :] * e[:, None]`, :153-155) */
+int pla_srct_weights_f64(const int64_t* k, int64_t g, int64_t m, int64_t j0, int64_t ncols, const int64_t* jmap,
+                         const double* e, const double* sgn, int with_sin, double* out, int64_t ldo, void* stream);
+int pla_gather_rows_scale_f64(const double* A, int64_t lda, const int64_t* perm, const double* e, int64_t rows,
+                              int64_t c0, int64_t nb, double* out, int64_t ldo, void* stream);
+
 /* ---------------------------------------------------------------- FP64 tensor-core GEMM (DMMA)
  * C[M x N] = alpha * op(A) * op(B) + beta * C, op(X) = X or X^T (transa/transb = 0/1).
  * Replaces the OpenBLAS dgemm behind `S @ A` (dense S; least_squares.py:303), `A @ S`, `A.T @ S`

@@ -90,6 +90,78 @@ class SkOpSJ:
         return sjlt_operator(n_rows, n_cols, rng, self.vec_nnz)
 
 
+def generate_srct(n_rows, n_cols, rng):
+    """Data of a subsampled randomized cosine transform, utils/sketching.py:106-115: the sampled
+    rows ``r`` (small_dim distinct indices), the sign vector ``e`` scaled by sqrt(big/small), and a
+    permutation of the long axis.  Generator call order: choice, random, permutation."""
+    big, small = max(n_rows, n_cols), min(n_rows, n_cols)
+    r = rng.choice(big, size=small, replace=False)
+    u = rng.random(big)
+    e = np.where(u > 0.5, 1.0, -1.0) * np.sqrt(big / small)
+    perm = rng.permutation(big)
+    return r, e, perm
+
+
+def apply_srct(r, e, mat, perm=None, forward=True):
+    """utils/sketching.py:118-176.  Forward: rows permuted, signs applied, orthonormal DCT-II along
+    axis 0, rows ``r`` kept.  Adjoint: zero-fill, inverse DCT, signs, inverse permutation."""
+    import scipy.fft as sfft
+    if forward:
+        x = mat if perm is None else mat[perm]
+        x = x * (e[:, None] if mat.ndim > 1 else e)
+        return sfft.dct(x, axis=0, norm='ortho')[r]
+    full = np.zeros((e.size,) + mat.shape[1:])
+    full[r] = mat
+    full = sfft.idct(full, axis=0, norm='ortho')
+    full = full * (e[:, None] if mat.ndim > 1 else e)
+    if perm is not None:
+        full = full[np.argsort(perm)]
+    return full
+
+
+class SrctOperator:
+    """What utils/sketching.py:179-201 returns (there a scipy LinearOperator): wide d x m operator
+    supporting ``S @ mat``, ``S.T @ mat``, ``.shape`` and carrying ``sketch_data = (r, e, perm)``."""
+
+    def __init__(self, shape, data, transposed=False):
+        self.shape, self.sketch_data, self.transposed = shape, data, transposed
+
+    def __matmul__(self, mat):
+        r, e, perm = self.sketch_data
+        return apply_srct(r, e, np.asarray(mat), perm, forward=not self.transposed)
+
+    @property
+    def T(self):
+        return SrctOperator(self.shape[::-1], self.sketch_data, not self.transposed)
+
+
+def srct_operator(n_rows, n_cols, rng):
+    """utils/sketching.py:179-201.  A tall request is the transpose of a wide construction; the
+    reference draws the data once before branching (:186) and again inside the recursive call (:200),
+    so the tall operator is built from the SECOND draw of the generator -- reproduced here."""
+    data = generate_srct(n_rows, n_cols, rng)
+    if n_cols >= n_rows:
+        return SrctOperator((n_rows, n_cols), data)
+    return srct_operator(n_cols, n_rows, rng).T
+
+
+def srct_dense(r, e, perm, m):
+    """The same operator as an explicit d x m matrix (definition of scipy's orthonormal DCT-II):
+    S[i, perm[j]] = e[j] * f(r_i) * cos(pi (2j+1) r_i / (2m)),  f(0) = sqrt(1/m), f(k>0) = sqrt(2/m)."""
+    j = np.arange(m)
+    C = np.cos(np.pi * np.outer(r, 2 * j + 1) / (2 * m)) * np.where(r == 0, np.sqrt(1.0 / m), np.sqrt(2.0 / m))[:, None]
+    S = np.zeros((r.size, m))
+    S[:, perm if perm is not None else j] = C * e
+    return S
+
+
+class SkOpTC:
+    """comps/sketchers/oblivious.py:68-72."""
+
+    def __call__(self, n_rows, n_cols, rng):
+        return srct_operator(n_rows, n_cols, rng)
+
+
 def sjlt_index_form(S):
     """Fixed-nnz index form of a wide SJLT: (rows[int32, n_cols x k], signs[int8, n_cols x k], k).
 

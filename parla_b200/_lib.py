@@ -38,6 +38,8 @@ SIGNATURES = {
     "pla_pcg_update_f64": (c_int, [c_i64, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "pla_sjlt_rmatvec_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_dbl, c_vp, c_vp]),
     "pla_gauss_rmatvec_f64": (c_int, [c_i64, c_i64, c_u64, c_i64, c_dbl, c_vp, c_vp, c_vp]),
+    "pla_srct_weights_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
+    "pla_gather_rows_scale_f64": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "pla_sjlt_plan_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pla_sjlt_plan_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "pla_sjlt_plan_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),

@@ -35,3 +35,12 @@ class SkOpSJ(SketchOpGen):
         return usk.sjlt_operator(n_rows, n_cols, rng, self.vec_nnz)
 
     exec = __call__
+
+
+class SkOpTC(SketchOpGen):
+    """SRCT (subsampled randomized cosine transform) generator (oblivious.py:68-72)."""
+
+    def __call__(self, n_rows, n_cols, rng):
+        return usk.srct_operator(n_rows, n_cols, rng)
+
+    exec = __call__

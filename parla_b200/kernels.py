@@ -366,6 +366,31 @@ def sjlt_generate(d, m, k, seed, col_offset=0, device="cuda"):
     return rows, signs
 
 
+# ---------------------------------------------------------------------------------------- SRCT
+def srct_weights(k, m, j0, ncols, jmap=None, e=None, sgn=None, with_sin=False, out=None):
+    """Cosine (and sine) weights of the orthonormal DCT-II for the frequencies ``k`` (int64 device vector) and
+    ``ncols`` positions j = jmap[j0 + c] (or j0 + c); see pla_srct_weights_f64."""
+    _req(k, "k", torch.int64)
+    g = k.numel()
+    width = (2 if with_sin else 1) * ncols
+    if out is None:
+        out = torch.empty(g, width, dtype=F64, device=k.device)
+    _lib.check(_lib.load().pla_srct_weights_f64(k.data_ptr(), g, int(m), int(j0), int(ncols), _p(jmap), _p(e), _p(sgn),
+                                                1 if with_sin else 0, out.data_ptr(), out.stride(0), _stream()),
+               "pla_srct_weights_f64")
+    return out
+
+
+def gather_rows_scale(A, perm, e, c0, nb, out):
+    """out[t, :nb] = e[t] * A[perm[t], c0:c0+nb]."""
+    A, lda = _rowmajor(A, "A")
+    rows = out.shape[0]
+    _lib.check(_lib.load().pla_gather_rows_scale_f64(A.data_ptr(), lda, _p(perm), _p(e), rows, int(c0), int(nb),
+                                                     out.data_ptr(), out.stride(0), _stream()),
+               "pla_gather_rows_scale_f64")
+    return out
+
+
 # ---------------------------------------------------------------------------------------- K3a / K6
 def geqrf(W, ncols_factor):
     """In-place Householder QR of the leading columns of the row-major W; returns tau."""

@@ -180,6 +180,183 @@ class DenseOperator(SketchOperator):
         return K.rmatvec(self.S, v)[:self.shape[1]].clone()
 
 
+class SRCTOperator(SketchOperator):
+    """Subsampled randomized cosine transform  S = R . DCT-II(ortho) . diag(e) . P  (d x m), the device
+    form of what parla/utils/sketching.py:179-201 returns.  ``r`` (d sampled frequencies), ``e`` (m scaled
+    signs) and ``perm`` (m) are the reference's ``sketch_data``.
+
+    ``S @ A`` never forms the m x n transform: only the d sampled rows are evaluated, as a pruned two-level
+    DCT (j = j1 + m1 j2) whose levels are FP64 tensor-core GEMMs -- 4 m n (m2 + d / m2) flops instead of the
+    2 d m n of a dense product.  When m has no usable divisor, A is not contiguous, or the operator is applied
+    to a row shard, the dense d x (rows) block of S is generated chunk by chunk and applied with the GEMM.
+    """
+
+    MAX_CHUNK_BYTES = 1 << 29
+
+    def __init__(self, n_rows, n_cols, r, e, perm, device=None):
+        self.device = _device(device)
+        self.shape = (int(n_rows), int(n_cols))
+        as_dev = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(
+            device=self.device, dtype=dt)
+        self.r, self.e = as_dev(r, torch.int64), as_dev(e, F64)
+        d, m = self.shape
+        self.perm = torch.arange(m, device=self.device) if perm is None else as_dev(perm, torch.int64)
+        self.invperm = torch.empty_like(self.perm)
+        self.invperm[self.perm] = torch.arange(m, device=self.device)
+        self._plans = {}
+
+    # ---- dense blocks of S (general path; also .T / to_dense for small operators)
+    def dense_columns(self, first, count):
+        """S[:, first:first+count]:  S[i, perm[j]] = e[j] c(r_i, j)."""
+        return K.srct_weights(self.r, self.shape[1], first, count, jmap=self.invperm, e=self.e)
+
+    def to_dense(self):
+        return self.dense_columns(0, self.shape[1])
+
+    def column_slice(self, first, count):
+        return _SRCTSlice(self, first, count)
+
+    def _apply_dense(self, A, b, out, first):
+        d = self.shape[0]
+        rows, n = A.shape
+        step = max(2, min(rows + rows % 2, self.MAX_CHUNK_BYTES // (8 * d)))
+        step -= step % 2
+        sb = torch.zeros(d, 1, dtype=F64, device=self.device) if b is not None else None
+        for t0 in range(0, rows, step):
+            t1 = min(rows, t0 + step)
+            Sd = self.dense_columns(first + t0, t1 - t0)
+            K.gemm(Sd, A[t0:t1], beta=0.0 if t0 == 0 else 1.0, out=out[:, :n])
+            if b is not None:
+                K.gemm(Sd, b[t0:t1].reshape(-1, 1), beta=1.0, out=sb)
+        if b is not None:
+            out[:, n] = sb[:, 0]
+        return out
+
+    # ---- pruned two-level DCT
+    def _plan(self, m2):
+        if m2 in self._plans:
+            return self._plans[m2]
+        d, m = self.shape
+        kap = self.r % (2 * m2)
+        fold = torch.where(kap <= m2, kap, 2 * m2 - kap)
+        sgn = torch.where(kap <= m2, 1.0, -1.0).to(F64)
+        order = torch.argsort(fold, stable=True)
+        fold_s = fold[order]
+        vals, counts = torch.unique_consecutive(fold_s, return_counts=True)
+        # level-1 table: rows [C_0, (C_1, S_1), ..., (C_{m2-1}, S_{m2-1}), C_{m2}] over j2 = 0 .. m2-1
+        kk = np.arange(m2 + 1)[:, None] * np.arange(m2)[None, :] % (2 * m2)
+        Cm, Sm = np.cos(np.pi * kk / m2), np.sin(np.pi * kk / m2)
+        F = np.empty((2 * m2, m2))
+        F[0], F[2 * m2 - 1] = Cm[0], Cm[m2]
+        F[1:2 * m2 - 1:2], F[2:2 * m2 - 1:2] = Cm[1:m2], Sm[1:m2]
+        plan = dict(order=order, k_sorted=self.r[order].contiguous(), sgn_sorted=sgn[order].contiguous(),
+                    groups=list(zip(vals.tolist(), counts.tolist())),
+                    F=torch.from_numpy(F).to(self.device))
+        self._plans[m2] = plan
+        return plan
+
+    @staticmethod
+    def choose_m2(m, d):
+        """Divisor of m in [4, 512] minimising the flop count m2 + d / m2 (None: use the dense path)."""
+        best = None
+        for m2 in range(4, 513):
+            if m % m2 == 0 and m // m2 >= 2:
+                cost = m2 + d / m2
+                if best is None or cost < best[0]:
+                    best = (cost, m2)
+        return None if best is None else best[1]
+
+    def _apply_factored(self, A, b, out, m2):
+        d, m = self.shape
+        n = A.shape[1]
+        m1 = m // m2
+        plan = self._plan(m2)
+        free = torch.cuda.mem_get_info(self.device)[0]
+        budget = min(free // 2, 48 << 30)
+        nb_max = max(2, int(budget // (24 * m)) // 2 * 2)
+        nblocks = -(-n // nb_max)
+        nb_max = -(-n // nblocks)
+        nb_max += nb_max % 2                                 # balanced, even-width column blocks
+        Zs = torch.empty(d, n + (1 if b is not None else 0), dtype=F64, device=self.device)
+        for c0 in range(0, n, nb_max):
+            nb = min(nb_max, n - c0)
+            last = c0 + nb >= n
+            extra = 1 if (b is not None and last) else 0
+            w = nb + extra
+            w += w % 2                                       # even leading dimension (16-byte GEMM loads)
+            Xp = torch.zeros(m, w, dtype=F64, device=self.device) if w != nb else \
+                torch.empty(m, w, dtype=F64, device=self.device)
+            K.gather_rows_scale(A, self.perm, self.e, c0, nb, Xp)
+            if extra:
+                Xp[:, nb] = self.e * b[self.perm]
+            Y = K.gemm(plan["F"], Xp.view(m2, m1 * w))       # level 1: (2 m2) x (m1 w)
+            del Xp
+            s0 = 0
+            for kappa, g in plan["groups"]:
+                ks, sg = plan["k_sorted"][s0:s0 + g], plan["sgn_sorted"][s0:s0 + g]
+                if kappa == 0 or kappa == m2:
+                    row = 0 if kappa == 0 else 2 * m2 - 1
+                    W2 = K.srct_weights(ks, m, 0, m1)
+                    Z = K.gemm(W2, Y[row].view(m1, w))
+                else:
+                    W2 = K.srct_weights(ks, m, 0, m1, sgn=sg, with_sin=True)
+                    Z = K.gemm(W2, Y[2 * kappa - 1:2 * kappa + 1].view(2 * m1, w))
+                Zs[s0:s0 + g, c0:c0 + nb + extra] = Z[:, :nb + extra]
+                s0 += g
+            del Y
+        out[:, :Zs.shape[1]].index_copy_(0, plan["order"], Zs)
+        return out
+
+    def sketch_into(self, A, b, out, row_offset=0, first=None):
+        first = row_offset if first is None else first
+        d, m = self.shape
+        rows, n = A.shape
+        whole = rows == m and first == 0
+        m2 = self.choose_m2(m, d) if (whole and A.is_contiguous()) else None
+        if m2 is None:
+            return self._apply_dense(A, b, out, first)
+        return self._apply_factored(A, b, out, m2)
+
+    def apply(self, A):
+        if A.shape[0] != self.shape[1]:
+            raise ValueError(f"shape mismatch: {self.shape} @ {tuple(A.shape)}")
+        out = torch.empty(self.shape[0], A.shape[1], dtype=F64, device=A.device)
+        return self.sketch_into(A, None, out)
+
+    def rmatvec(self, v, m_local=None, row_offset=0):
+        """S[:, off:off+m_local]^T @ v  (`apply_srct(..., forward=False)` on one vector, sketching.py:162-175)."""
+        d, m = self.shape
+        m_local = m if m_local is None else m_local
+        out = torch.empty(m_local, dtype=F64, device=self.device)
+        step = max(2, min(K.PASS_MAX_N, self.MAX_CHUNK_BYTES // (8 * d)))
+        for t0 in range(0, m_local, step):
+            t1 = min(m_local, t0 + step)
+            Sd = self.dense_columns(row_offset + t0, t1 - t0)
+            out[t0:t1] = K.rmatvec(Sd, v)[:t1 - t0]
+        return out
+
+
+class _SRCTSlice(SketchOperator):
+    """Columns [first, first+count) of an SRCTOperator (what a row shard of A meets)."""
+
+    def __init__(self, base, first, count):
+        self.base, self.first = base, int(first)
+        self.shape = (base.shape[0], int(count))
+
+    def sketch_into(self, A, b, out, row_offset=0):
+        return self.base.sketch_into(A, b, out, first=self.first)
+
+    def apply(self, A):
+        out = torch.empty(self.shape[0], A.shape[1], dtype=F64, device=A.device)
+        return self.sketch_into(A, None, out)
+
+    def to_dense(self):
+        return self.base.dense_columns(self.first, self.shape[1])
+
+    def rmatvec(self, v, m_local=None, row_offset=0):
+        return self.base.rmatvec(v, m_local=self.shape[1], row_offset=self.first)
+
+
 def as_device_operator(S, device=None):
     """Accept whatever a ``sketch_op_gen`` returned: one of our operators, a numpy ndarray, a torch
     tensor, or a scipy.sparse SJLT (fixed nnz per column, +-c values) as built by the reference."""
@@ -190,6 +367,13 @@ def as_device_operator(S, device=None):
         return DenseOperator(S.to(device=device, dtype=F64))
     if isinstance(S, np.ndarray):
         return DenseOperator(torch.from_numpy(np.ascontiguousarray(S, dtype=np.float64)).to(device))
+    data = getattr(S, "sketch_data", None)                # the reference's SRCT LinearOperator (sketching.py:198)
+    if data is not None and not getattr(S, "transposed", False):
+        r, e, perm = data
+        return SRCTOperator(S.shape[0], S.shape[1], r, e, perm, device)
+    inner = getattr(S, "A", None) if data is None else S.T      # scipy's _TransposedLinearOperator / oracle .T
+    if inner is not None and getattr(inner, "sketch_data", None) is not None:
+        return DenseOperator(as_device_operator(inner, device).to_dense().T.contiguous())
     try:
         import scipy.sparse as sps
     except ImportError:                                   # pragma: no cover
@@ -229,4 +413,41 @@ def sjlt_operator(n_rows, n_cols, rng, vec_nnz=8, device=None):
         rows, signs = K.sjlt_generate(n_rows, count, k, seed, col_offset=first, device=device)
         return SJLTOperator(n_rows, rows, signs)
     wide = sjlt_operator(n_cols, n_rows, np.random.default_rng(seed), vec_nnz, device)
+    return DenseOperator(wide.to_dense().T.contiguous())
+
+
+def generate_srct(n_rows, n_cols, rng, device=None):
+    """parla/utils/sketching.py:106-115: (r, e, perm) with r = small_dim distinct indices of the long axis,
+    e = +-sqrt(big/small), perm a permutation of the long axis -- drawn on the device from one key of ``rng``."""
+    seed, _ = _draw_key(rng)
+    device = _device(device)
+    big, small = max(n_rows, n_cols), min(n_rows, n_cols)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    r = torch.randperm(big, generator=gen, device=device)[:small].contiguous()
+    e = torch.where(torch.rand(big, generator=gen, device=device, dtype=F64) > 0.5, 1.0, -1.0).to(F64)
+    e = e * math.sqrt(big / small)
+    perm = torch.randperm(big, generator=gen, device=device)
+    return r, e, perm
+
+
+def apply_srct(r, e, mat, perm=None, forward=True):
+    """parla/utils/sketching.py:118-176 for device tensors (1-D or 2-D ``mat``)."""
+    m = e.numel()
+    S = SRCTOperator(r.numel(), m, r, e, perm, mat.device)
+    if forward:
+        return S @ mat
+    if mat.dim() == 1:
+        return S.rmatvec(mat)
+    return K.gemm(S.to_dense(), mat, transa=True)
+
+
+def srct_operator(n_rows, n_cols, rng, device=None):
+    """parla/utils/sketching.py:179-201.  Wide: an SRCTOperator.  Tall: the transpose of the wide construction
+    as a dense device matrix (only used as a small test matrix, e.g. by RS1)."""
+    rng = np.random.default_rng(rng)
+    r, e, perm = generate_srct(n_rows, n_cols, rng, device)
+    if n_cols >= n_rows:
+        return SRCTOperator(n_rows, n_cols, r, e, perm, device)
+    wide = srct_operator(n_cols, n_rows, rng, device)
     return DenseOperator(wide.to_dense().T.contiguous())

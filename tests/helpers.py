@@ -122,6 +122,17 @@ def sps_algorithm(mod, fx, gen):
     return a
 
 
+SRCT_FIXTURES = ["spo_srct_qr_600x40", "spo_srct_qr_ridge_600x40", "spo_srct_svd_600x40", "spo_srct_chol_600x40",
+                 "spo_srct_qr_prime_1009x33", "spo_srct_qr_cond1e4_4096x96"]
+
+
+def srct_from_fixture(fx, d, m):
+    """The reference's SRCT operator of a fixture, as the oracle's operator object (carries sketch_data)."""
+    from oracle import parla_oracle as orc
+    e = fx["S_e_sign"].astype(np.float64) * float(fx["S_e_scale"])
+    return orc.SrctOperator((d, m), (fx["S_r"].astype(np.int64), e, fx["S_perm"].astype(np.int64)))
+
+
 class Replay:
     """sketch_op_gen that hands back a prerecorded operator (reference S replayed on the GPU path)."""
 
