@@ -192,6 +192,7 @@ class SRCTOperator(SketchOperator):
     """
 
     MAX_CHUNK_BYTES = 1 << 29
+    STAGE_TIMINGS = None      # set to a dict to accumulate synchronised per-stage seconds (diagnostics only)
 
     def __init__(self, n_rows, n_cols, r, e, perm, device=None):
         self.device = _device(device)
@@ -271,40 +272,75 @@ class SRCTOperator(SketchOperator):
         n = A.shape[1]
         m1 = m // m2
         plan = self._plan(m2)
-        free = torch.cuda.mem_get_info(self.device)[0]
-        budget = min(free // 2, 48 << 30)
-        nb_max = max(2, int(budget // (24 * m)) // 2 * 2)
+        # memory this call may use: what the driver reports free + what torch's allocator holds unused
+        free = torch.cuda.mem_get_info(self.device)[0] + torch.cuda.memory_reserved(self.device) \
+            - torch.cuda.memory_allocated(self.device)
+        w2_bytes = 16 * d * m1                               # all level-2 weights, kept across column blocks
+        keep_w2 = w2_bytes <= free // 8
+        budget = min((free - (w2_bytes if keep_w2 else 0)) // 2, 64 << 30)
+        nb_max = max(2, int(budget // (24 * m)) // 2 * 2)    # Xp (m x w) + Y (2m x w) live together
         nblocks = -(-n // nb_max)
-        nb_max = -(-n // nblocks)
-        nb_max += nb_max % 2                                 # balanced, even-width column blocks
+        nb = -(-n // nblocks)
+        if -(-nb // 128) * 128 <= nb_max:
+            nb = -(-nb // 128) * 128                         # whole GEMM tiles along N
+        nb += nb % 2
+        blocks = [(c0, min(nb, n - c0), False) for c0 in range(0, n, nb)]
+        if b is not None:
+            blocks.append((n, 1, True))                      # the right-hand side is its own (2-wide, padded) block
         Zs = torch.empty(d, n + (1 if b is not None else 0), dtype=F64, device=self.device)
-        for c0 in range(0, n, nb_max):
-            nb = min(nb_max, n - c0)
-            last = c0 + nb >= n
-            extra = 1 if (b is not None and last) else 0
-            w = nb + extra
-            w += w % 2                                       # even leading dimension (16-byte GEMM loads)
-            Xp = torch.zeros(m, w, dtype=F64, device=self.device) if w != nb else \
-                torch.empty(m, w, dtype=F64, device=self.device)
-            K.gather_rows_scale(A, self.perm, self.e, c0, nb, Xp)
-            if extra:
-                Xp[:, nb] = self.e * b[self.perm]
+        cache = {}
+        rec = SRCTOperator.STAGE_TIMINGS
+
+        def lap(name, t0):
+            if rec is None:
+                return 0.0
+            import time
+            torch.cuda.synchronize()
+            now = time.time()
+            rec[name] = rec.get(name, 0.0) + now - t0
+            return now
+        t0 = 0.0
+        if rec is not None:
+            import time
+            torch.cuda.synchronize()
+            t0 = time.time()
+
+        def weights(idx, ks, sg, both):
+            if idx not in cache:
+                W2 = K.srct_weights(ks, m, 0, m1, sgn=sg if both else None, with_sin=both)
+                if not keep_w2:
+                    return W2
+                cache[idx] = W2
+            return cache[idx]
+
+        for c0, width, is_rhs in blocks:
+            w = width + width % 2                            # even leading dimension (16-byte GEMM loads)
+            Xp = torch.empty(m, w, dtype=F64, device=self.device)
+            if is_rhs:
+                Xp[:, 0] = self.e * b[self.perm]
+                Xp[:, 1] = 0.0
+            else:
+                if w != width:
+                    Xp[:, width:] = 0.0
+                K.gather_rows_scale(A, self.perm, self.e, c0, width, Xp)
+            t0 = lap("gather", t0)
             Y = K.gemm(plan["F"], Xp.view(m2, m1 * w))       # level 1: (2 m2) x (m1 w)
             del Xp
+            t0 = lap("level1", t0)
             s0 = 0
-            for kappa, g in plan["groups"]:
+            for idx, (kappa, g) in enumerate(plan["groups"]):
                 ks, sg = plan["k_sorted"][s0:s0 + g], plan["sgn_sorted"][s0:s0 + g]
                 if kappa == 0 or kappa == m2:
                     row = 0 if kappa == 0 else 2 * m2 - 1
-                    W2 = K.srct_weights(ks, m, 0, m1)
-                    Z = K.gemm(W2, Y[row].view(m1, w))
+                    Z = K.gemm(weights(idx, ks, sg, False), Y[row].view(m1, w))
                 else:
-                    W2 = K.srct_weights(ks, m, 0, m1, sgn=sg, with_sin=True)
-                    Z = K.gemm(W2, Y[2 * kappa - 1:2 * kappa + 1].view(2 * m1, w))
-                Zs[s0:s0 + g, c0:c0 + nb + extra] = Z[:, :nb + extra]
+                    Z = K.gemm(weights(idx, ks, sg, True), Y[2 * kappa - 1:2 * kappa + 1].view(2 * m1, w))
+                Zs[s0:s0 + g, c0:c0 + width] = Z[:, :width]
                 s0 += g
             del Y
+            t0 = lap("level2+weights", t0)
         out[:, :Zs.shape[1]].index_copy_(0, plan["order"], Zs)
+        lap("scatter", t0)
         return out
 
     def sketch_into(self, A, b, out, row_offset=0, first=None):

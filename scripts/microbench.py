@@ -137,6 +137,20 @@ def main():
                               "iters": log.iters, "passes": log.passes_over_A,
                               "ms_per_iter": round(1e3 * log.time_iterate / max(log.iters, 1), 3),
                               "err_last": float(log.errors[-1])}), flush=True)
+    if want("srct"):
+        # SRCT sketch [S A | S b] at the headline size (pruned two-level DCT on DMMA GEMMs)
+        S = rla.srct_operator(d, m, 5)
+        W = torch.zeros(d, n + 2, dtype=torch.float64, device="cuda")
+        t, tm = timeit(lambda: S.sketch_into(A, u, W[:, :n + 1]), warm=1, reps=2)
+        m2 = S.choose_m2(m, d)
+        report("srct_sketch", t, tm, bytesA, flops=4.0 * m * (n + 1) * (m2 + d / m2) if m2 else 2.0 * d * m * (n + 1),
+               extra={"d": d, "m2": m2, "dense_equiv_flops": 2.0 * d * m * (n + 1)})
+        from parla_b200.utils.sketching import SRCTOperator
+        SRCTOperator.STAGE_TIMINGS = {}
+        S.sketch_into(A, u, W[:, :n + 1])
+        print(json.dumps({"srct_stage_seconds": {k: round(v, 4) for k, v in SRCTOperator.STAGE_TIMINGS.items()}}), flush=True)
+        SRCTOperator.STAGE_TIMINGS = None
+        del S, W
     if want("sps"):
         # saddle-point system at the headline size: SPS2 (LSQR) and SPS1 (PCG; one fused Gram pass per iteration)
         x0 = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
