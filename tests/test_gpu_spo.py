@@ -235,3 +235,35 @@ def test_spo_degenerate_inputs(rla):
     assert log.errors.size - 1 <= 3
     xs, _ = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(dev(A), dev(b), 0.0, 1e-12, 50, 1, logging=False)
     assert np.linalg.norm(xs.cpu().numpy() - np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-10
+
+
+def test_svd_right_precond_gram_route_and_fallback(rla):
+    """preconditioning.py:70-79 for n >= 512: well-conditioned sketches take the Gram/eigh route (same
+    M, U, sigma, Vh as the cuSOLVER SVD), ill-conditioned and rank-deficient ones fall back to it."""
+    from parla_b200.comps import preconditioning as rpc
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 640
+    X = torch.randn(3 * n, n, dtype=torch.float64, device="cuda", generator=g)
+    for scale, expect_fast in ((None, True), (torch.logspace(0, -6, n, dtype=torch.float64, device="cuda"), False)):
+        Xs = X if scale is None else X * scale
+        assert (rpc._svd_via_gram(Xs) is not None) == expect_fast
+        M, U, s, Vh = rpc.svd_right_precond(Xs)
+        s_ref = torch.linalg.svdvals(Xs)
+        assert float(((s.sort(descending=True)[0] - s_ref).abs() / s_ref).max()) <= 1e-10
+        assert float(torch.linalg.norm((U * s) @ Vh - Xs) / torch.linalg.norm(Xs)) <= 1e-12
+        eye = torch.eye(n, dtype=torch.float64, device="cuda")
+        assert float(torch.linalg.norm(U.T @ U - eye)) <= 1e-9 and float(torch.linalg.norm(Vh @ Vh.T - eye)) <= 1e-9
+        assert float(torch.linalg.norm(Xs @ M - U)) <= 1e-9 * n
+    Xr = X.clone()
+    Xr[:, -5:] = Xr[:, :5]                                   # rank n - 5: truncation must come from the true SVD
+    assert rpc._svd_via_gram(Xr) is None
+    M, U, s, Vh = rpc.svd_right_precond(Xr)
+    assert M.shape == (n, n - 5) and s.numel() == n - 5
+    # the driver: mode 'svd' (fast route) gives the same x as mode 'qr'
+    A = torch.randn(20000, n, dtype=torch.float64, device="cuda", generator=g)
+    b = torch.randn(20000, dtype=torch.float64, device="cuda", generator=g)
+    x_svd, log_svd = rla.SPO(rla.SkOpSJ(8), 4, 'svd')(A, b, 0.0, 1e-12, 100, 5)
+    x_qr, log_qr = rla.SPO(rla.SkOpSJ(8), 4, 'qr')(A, b, 0.0, 1e-12, 100, 5)
+    assert float(torch.linalg.vector_norm(x_svd - x_qr) / torch.linalg.vector_norm(x_qr)) <= 1e-10
+    assert abs(log_svd.iters - log_qr.iters) <= 1
+    assert np.allclose(log_svd.errors[:10], log_qr.errors[:10], rtol=1e-6)      # |M'A'r| is rotation invariant
