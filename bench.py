@@ -47,11 +47,19 @@ def parse():
     return ap.parse_args()
 
 
+def metric_name(a):
+    """BASELINE.json's metric for the default workload; a descriptive name for any other shape / mode."""
+    if (a.m, a.n, a.mode) == (1 << 22, 2048, 'qr'):
+        return METRIC
+    return f"{'sap1' if a.mode == 'qr' else 'sap2' if a.mode == 'svd' else 'spo_chol'}_lsq_solve_time_{a.m}x{a.n}_per_gpu_fp64"
+
+
 def workload_name(a, world):
     return (f"{'SAP1' if a.mode == 'qr' else 'SAP2' if a.mode == 'svd' else 'SPO'}/SPO(mode={a.mode}) overdetermined least squares, {a.m}x{a.n} fp64 per GPU "
             f"(m_global={a.m * world}), {a.sketch.upper()} sketch"
             f"{' k=8' if a.sketch == 'sjlt' else ''}, d=4n={SF * a.n}, tol=1e-12, iter_lim=100 "
-            f"[BASELINE.json configs[1]]")
+            + ("[BASELINE.json configs[1]]" if (a.m, a.n, a.mode) == (1 << 22, 2048, 'qr') else
+               "[BASELINE.json configs[4] shape]" if a.n == 4096 else "[non-default shape]"))
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -103,7 +111,7 @@ def run_reference_arm(a):
               f"step (measured {sum(last[k] for k in ('sketch','factor','presolve','iterate')):.2f} s, {last['iters']} "
               f"iterations); sketch/presolve/LSQR phases are O(m) and scaled x{a.m * world // a.cpu_rows}, the "
               f"{SF * a.n}x{a.n} QR is not scaled")
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    line = {"impl": "reference", "metric": metric_name(a), "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * (time.time() - t_all) / max(a.steps, 1),
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a, world), "timing": "wall clock on host"},
@@ -308,11 +316,11 @@ def run_gpu_arm(a):
                           f"QR {ph['factor']:.2f} s, presolve {ph['presolve']:.2f} s, LSQR {ph['iterate']:.2f} s "
                           f"({ph['iters']} its); O(m) phases scaled x{m // a.cpu_rows}, QR unscaled")}
 
-    line = {"metric": METRIC, "value": t_step, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    line = {"metric": metric_name(a), "value": t_step, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * t_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a, world), "parallelism": f"row-sharded x{world}",
-                       "l2": "inputs (64 GiB per GPU) are far larger than the 126 MB L2; no flush needed",
+                       "l2": f"inputs ({a.m * a.n * 8 / 2 ** 30:.0f} GiB per GPU) are far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events around the K solves, max over ranks"},
             "phases_s": phases, "check": check, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
