@@ -403,13 +403,6 @@ def as_device_operator(S, device=None):
         return DenseOperator(S.to(device=device, dtype=F64))
     if isinstance(S, np.ndarray):
         return DenseOperator(torch.from_numpy(np.ascontiguousarray(S, dtype=np.float64)).to(device))
-    data = getattr(S, "sketch_data", None)                # the reference's SRCT LinearOperator (sketching.py:198)
-    if data is not None and not getattr(S, "transposed", False):
-        r, e, perm = data
-        return SRCTOperator(S.shape[0], S.shape[1], r, e, perm, device)
-    inner = getattr(S, "A", None) if data is None else S.T      # scipy's _TransposedLinearOperator / oracle .T
-    if inner is not None and getattr(inner, "sketch_data", None) is not None:
-        return DenseOperator(as_device_operator(inner, device).to_dense().T.contiguous())
     try:
         import scipy.sparse as sps
     except ImportError:                                   # pragma: no cover
@@ -425,6 +418,13 @@ def as_device_operator(S, device=None):
             signs = torch.from_numpy(np.sign(C.data).reshape(-1, k).astype(np.int8)).to(device)
             return SJLTOperator(C.shape[0], rows, signs, validate=True)
         return DenseOperator(torch.from_numpy(np.asarray(C.todense(), dtype=np.float64)).to(device))
+    data = getattr(S, "sketch_data", None)                # the reference's SRCT LinearOperator (sketching.py:198)
+    if data is not None and not getattr(S, "transposed", False):
+        r, e, perm = data
+        return SRCTOperator(S.shape[0], S.shape[1], r, e, perm, device)
+    inner = getattr(S, "A", None) if data is None else S.T      # scipy's _TransposedLinearOperator / oracle .T
+    if inner is not None and getattr(inner, "sketch_data", None) is not None:
+        return DenseOperator(as_device_operator(inner, device).to_dense().T.contiguous())
     raise TypeError(f"unsupported sketching operator type {type(S)!r}")
 
 

@@ -110,3 +110,35 @@ def test_row_sharded_allreduce_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert list(out) == [1, 1]
+
+
+def test_saddle_and_srct_public_names():
+    for name in ("SPS1", "SPS2", "sps", "SaddleSolver", "PcSS1", "PcSS2", "pcss1", "pcss2", "pcg", "SPU1",
+                 "SkOpTC", "srct_operator", "generate_srct", "apply_srct"):
+        assert hasattr(rla, name), name
+    for cls in (rla.SPS1, rla.SPS2, rla.PcSS1, rla.PcSS2, rla.SkOpTC, rla.SPU1):
+        assert cls.exec is cls.__call__
+    a = rla.SPS1(rla.SkOpSJ(), 3)                          # saddlesys.py:120-129 defaults
+    assert isinstance(a.iterative_solver, rla.PcSS1) and a.nystrom_strategy == 'left'
+    assert isinstance(rla.SPS2(rla.SkOpSJ(), 3, None).iterative_solver, rla.PcSS2)
+    with pytest.raises(ValueError):                        # saddlesys.py:84 (raised before any device work)
+        rla.sps(None, None, None, 0.0, 1e-8, 10, 0, method='nope')
+    with pytest.raises(NotImplementedError):               # abstract interfaces
+        rla.SaddleSolver()(None, None, None, 0.0, 1e-8, 10, 0, True)
+    with pytest.raises(NotImplementedError):
+        rla.PrecondSaddleSolver()(None, None, None, 0.0, 1e-8, 10, None, False, None)
+
+
+def test_srct_two_level_plan_choice():
+    """The divisor m2 of m that minimises m2 + d / m2 (flops of the two DCT levels); None -> dense blocks."""
+    from parla_b200.utils.sketching import SRCTOperator
+    assert SRCTOperator.choose_m2(1 << 22, 8192) in (64, 128)
+    assert SRCTOperator.choose_m2(100000, 10000) == 100
+    assert SRCTOperator.choose_m2(1009, 132) is None       # prime row count: no factorisation
+    assert SRCTOperator.choose_m2(2 * 1009, 100) is None   # only divisor in range would be 2 < 4
+    m2 = SRCTOperator.choose_m2(6000, 300)
+    assert 6000 % m2 == 0 and 4 <= m2 <= 512
+    # level-1 table of the oracle-checked definition: cos/sin of pi * kappa * j2 / m2 in the row layout used
+    m2 = 8
+    kk = np.arange(m2 + 1)[:, None] * np.arange(m2)[None, :]
+    assert np.allclose(np.cos(np.pi * (kk % (2 * m2)) / m2), np.cos(np.pi * kk / m2), atol=1e-15)
