@@ -93,10 +93,26 @@ def cpu_threads():
     return len(os.sched_getaffinity(0)), "unknown BLAS"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin the CPU arm to one BLAS thread:
+    lift the limit to every core this process may run on (OpenBLAS accepts this at run time)."""
+    global _THREAD_LIMITER
+    try:
+        import numpy, scipy.linalg, scipy.sparse       # noqa: F401,E401  (load the BLAS libraries first)
+        from threadpoolctl import threadpool_limits
+        _THREAD_LIMITER = threadpool_limits(limits=len(os.sched_getaffinity(0)), user_api="blas")   # keep it alive
+    except Exception:
+        pass
+
+
+_THREAD_LIMITER = None
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     world = max(1, a.gpus)
     for _ in range(a.warmup):
         cpu_solve_sample(a.n, a.cpu_rows)
@@ -309,6 +325,7 @@ def run_gpu_arm(a):
 
     cpu = None
     if world == 1 and not a.no_cpu:
+        use_all_host_threads()
         ph = cpu_solve_sample(n, a.cpu_rows)
         cores, blas = cpu_threads()
         cpu = {"value": cpu_extrapolate(ph, a.cpu_rows, m), "unit": UNIT, "cores": cores, "kind": "port",
