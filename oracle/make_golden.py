@@ -264,6 +264,39 @@ def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pa
                         approx_probe=approx_ref[::max(1, m // 16), ::max(1, n // 16)])
 
 
+def qb3_evd2_cases():
+    """QB3 (comps/qb.py:484-598; test_qb.py:414-489) and EVD2 (drivers/evd.py:290-381; test_evd.py:159-183)."""
+    import parla.comps.qb as rqb
+    import parla.drivers.evd as revd
+    import parla.comps.sketchers.aware as raw
+    for name, m, n, rank, k, blk, tol, seed in (("qb3_200x50", 200, 50, 30, 28, 4, np.nan, 41),
+                                                ("qb3_tol_200x50", 200, 50, 30, 28, 4, 2e-2, 42),
+                                                ("qb3_wide_60x240", 60, 240, 25, 24, 5, np.nan, 43)):
+        A = orc.exponent_spectrum(m, n, rank, np.random.default_rng(seed), 3.0)
+        Qr, Br = rqb.QB3(raw.RS1(rsko.SkOpGA(), 0, rulaw.orth, 1), blk)(A, k, tol, np.random.default_rng(7))
+        Qo, Bo = orc.QB3(orc.RS1(orc.SkOpGA(), 0, orc.orth, 1), blk)(A, k, tol, np.random.default_rng(7))
+        ap = Qr @ Br
+        print(f"{name:28s} QB3 cols {Qr.shape[1]}  d(QB) {relerr(Qo @ Bo, ap):.2e}  |A-QB|/|A| {relerr(ap, A):.2e}")
+        assert Qr.shape == Qo.shape and relerr(Qo @ Bo, ap) < 1e-10
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="qb3", m=m, n=n, rank=rank, k=k, blk=blk, tol=tol,
+                            seed=seed, qb_cols=Qr.shape[1], approx_fro=np.linalg.norm(ap),
+                            err_fro=np.linalg.norm(A - ap), A_sha=digest(A),
+                            approx_probe=ap[::max(1, m // 16), ::max(1, n // 16)])
+    for name, n, rank, k, over, seed in (("evd2_120_over0", 120, 40, 30, 0, 44), ("evd2_120_over5", 120, 40, 30, 5, 45),
+                                         ("evd2_120_exact", 120, 20, 17, 5, 46)):
+        B0 = orc.rand_low_rank(n, rank, rank, np.random.default_rng(seed))
+        A = B0 @ B0.T
+        A = 0.5 * (A + A.T)
+        Vr, lr = revd.EVD2(raw.RS1(rsko.SkOpGA(), 1, rulaw.orth, 1))(A, k, np.nan, over, np.random.default_rng(7))
+        Vo, lo = orc.EVD2(orc.RS1(orc.SkOpGA(), 1, orc.orth, 1))(A, k, np.nan, over, np.random.default_rng(7))
+        ap = (Vr * lr) @ Vr.T
+        print(f"{name:28s} EVD2 rank {lr.size}  d(approx) {relerr((Vo * lo) @ Vo.T, ap):.2e}  |A-VLV'|/|A| {relerr(ap, A):.2e}")
+        assert lr.shape == lo.shape and relerr((Vo * lo) @ Vo.T, ap) < 1e-10
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="evd2", n=n, rank=rank, k=k, over=over, seed=seed,
+                            spec=lr, approx_fro=np.linalg.norm(ap), err_fro=np.linalg.norm(A - ap), A_sha=digest(A),
+                            approx_probe=ap[::max(1, n // 16), ::max(1, n // 16)])
+
+
 def philox_case():
     """Known-answer vectors for Philox4x32-10 (Random123 kat_vectors) + oracle stream samples."""
     from oracle import philox_ref as ph
@@ -282,6 +315,9 @@ def philox_case():
 
 
 if __name__ == "__main__":
+    if "--only-qb3" in sys.argv:
+        qb3_evd2_cases()
+        sys.exit(0)
     if "--only-srct" in sys.argv:
         srct_cases()
         sys.exit(0)
@@ -314,4 +350,5 @@ if __name__ == "__main__":
     spu_case("spu1_sjlt_2000x96", 2000, 96, 32, cond=1e5)
     sps_cases()
     srct_cases()
+    qb3_evd2_cases()
     print("golden fixtures written to", OUT)

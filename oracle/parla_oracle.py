@@ -912,6 +912,70 @@ class QB2:
         return Q, B
 
 
+class QB3:
+    """Single-pass-style blocked QB from the sketches G = A S and H = A'G, comps/qb.py:484-598
+    ([YGL:2018, Algorithm 4] with an arbitrary row sketcher).  tol > 0 enables early stopping."""
+
+    def __init__(self, sk_op, blk):
+        self.sk_op = sk_op
+        self.blk = blk
+
+    def __call__(self, A, k, tol, rng):
+        assert k > 0 and k < min(A.shape)                         # :555-556
+        use_tol = (not np.isnan(tol)) and tol > 0
+        if use_tol:
+            sq_norm = np.linalg.norm(A, 'fro') ** 2
+            stop_at = sq_norm * tol ** 2
+        rng = np.random.default_rng(rng)
+        S = self.sk_op(A, k, rng)
+        if not isinstance(S, np.ndarray):
+            raise RuntimeError(f"QB3 needs a dense sketching matrix, got {type(S)}")      # :568-574
+        G = A @ S
+        H = A.T @ G
+        m, n = A.shape
+        Q, B = np.empty((m, 0)), np.empty((0, n))
+        for lo in range(0, k, self.blk):                          # :577-597
+            hi = min(lo + self.blk, k)
+            BS = B @ S[:, lo:hi]
+            Y = G[:, lo:hi] - Q @ BS
+            Qi, Ri = sla.qr(Y, mode='economic')
+            Qi = Qi - Q @ (Q.T @ Qi)
+            Qi, Rhat = sla.qr(Qi, mode='economic')
+            Ri = Rhat @ Ri
+            Bi = H[:, lo:hi].T - (Y.T @ Q) @ B - BS.T @ B
+            Bi = sla.solve_triangular(Ri, Bi, trans='T', lower=False)
+            Q, B = np.hstack((Q, Qi)), np.vstack((B, Bi))
+            if use_tol:
+                sq_norm -= np.linalg.norm(Bi, 'fro') ** 2
+                if sq_norm <= stop_at:
+                    break
+        return Q, B
+
+
+class EVD2:
+    """Fixed-rank PSD eigendecomposition from a regularised Nystrom approximation, drivers/evd.py:290-381
+    (Tropp, Yurtsever, Udell, Cevher 2017, Algorithm 3)."""
+
+    def __init__(self, sk_op):
+        self.sk_op = sk_op
+
+    def __call__(self, A, k, tol, over, rng):
+        n = A.shape[0]
+        assert k > 0 and k < n                                    # :352-354
+        if not np.isnan(tol):
+            warnings.warn("EVD2 cannot control the approximation error; 'tol' is ignored.")
+        rng = np.random.default_rng(rng)
+        S = self.sk_op(A, k + over, rng)
+        Y = A @ S
+        nu = np.sqrt(n) * EPS * np.linalg.norm(Y)                 # :365 temporary regularisation
+        Y = Y + nu * S
+        R = sla.cholesky(S.T @ Y, lower=False)
+        Bm = sla.solve_triangular(R, Y.T, lower=False, trans='T').T
+        V, sigma, _ = sla.svd(Bm, full_matrices=False)
+        r = min([k] + [i for i in range(k - 1) if sigma[i + 1] ** 2 <= nu])       # :373-377
+        return V[:, :r], (sigma ** 2)[:r] - nu
+
+
 class SVD1:
     """drivers/svd.py:126-176."""
 

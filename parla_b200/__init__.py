@@ -9,7 +9,7 @@ from .utils.sketching import (gaussian_operator, sjlt_operator, srct_operator, g
 from .utils.linalg_wrappers import orth
 from .comps.sketchers.oblivious import SkOpGA, SkOpSJ, SkOpTC, SketchOpGen
 from .comps.sketchers.aware import RS1, RowSketcher
-from .comps.qb import QB1, QB2, QBDecomposer
+from .comps.qb import QB1, QB2, QB3, QBDecomposer
 from .comps.rangefinders import RF1, RangeFinder
 from .comps.determiter.logging import SketchAndPrecondLog
 from .comps.determiter.saddle import PcSS1, PcSS2, PrecondSaddleSolver, pcss1, pcss2
@@ -17,5 +17,5 @@ from .comps.determiter.pcg import pcg
 from .drivers.least_squares import SPO, SSO1, OverLstsqSolver, SPU1, UnderLstsqSolver
 from .drivers.saddlesys import SPS1, SPS2, SaddleSolver, sps
 from .drivers.svd import SVD1, SVDecomposer
-from .drivers.evd import EVD1, EVDecomposer
+from .drivers.evd import EVD1, EVD2, EVDecomposer
 from .parallel import RowSharded

@@ -1,5 +1,5 @@
 """QB decompositions.  Mirrors parla/comps/qb.py: interface (:241-283), ``QB1`` (:286-352),
-``QB2`` (:355-482) and ``project_out`` (:603-613).
+``QB2`` (:355-482), ``QB3`` (:484-598) and ``project_out`` (:603-613).
 
 QB2 preallocates Q and B (the reference re-stacks them every block, :473-474) and deflates A in
 place with one rank-blk DMMA update (:475).
@@ -112,5 +112,78 @@ class QB2(QBDecomposer):
             if cols >= k:
                 break
         return q_view(0, cols), B[:cols]
+
+    exec = __call__
+
+
+class QB3(QBDecomposer):
+    """Blocked QB from the two sketches G = A S and H = A' G (qb.py:484-598): after those two passes over A
+    everything is m x blk / n x blk work (DMMA GEMMs, Householder QR of the blocks, blk x blk solves)."""
+
+    TOL_CONTROL = 'early stopping'
+
+    def __init__(self, sk_op, blk: int):
+        self.sk_op = sk_op
+        self.blk = blk
+
+    def __call__(self, A, k, tol, rng):
+        assert k > 0                                               # qb.py:555-556
+        assert k < min(A.shape)
+        use_tol = not np.isnan(tol) and tol > 0
+        if use_tol:
+            sq_norm_A = float(distla.sumsq_all(A))
+            abs_sq_tol = sq_norm_A * tol ** 2
+        rng = np.random.default_rng(rng)
+        blk = self.blk
+        S = self.sk_op(A, k, rng)
+        if not isinstance(S, torch.Tensor):                        # :568-574
+            msg = """
+            This implementation requires the sketching routine to return a
+            dense matrix, as represented by a device tensor. We received a
+            matrix of type %s
+            """ % str(type(S))
+            raise RuntimeError(msg)
+        S = S.contiguous()
+        G = distla.mm(A, S)                                        # :575  m x k (row-sharded like A)
+        H = distla.mm_t(A, G)                                      # :576  n x k (replicated)
+        m, n = A.shape
+        sharded = isinstance(A, RowSharded)
+        m_loc = A.local.shape[0] if sharded else m
+        Qbuf = torch.empty(m_loc, k, dtype=F64, device=A.device)
+        B = torch.empty(k, n, dtype=F64, device=A.device)
+        Gl = distla.local(G)
+
+        def wrap(v):
+            return RowSharded(v, A.row_offset, A.m_global, A.group) if sharded else v
+
+        cols = 0
+        for lo in range(0, k, blk):                                # :577-597
+            hi = min(lo + blk, k)
+            Si = S[:, lo:hi].contiguous()
+            Q, Bc = wrap(Qbuf[:, :cols]), B[:cols]
+            Yi_loc = Gl[:, lo:hi].contiguous()
+            if cols > 0:
+                BSi = K.gemm(Bc, Si)                               # cols x b
+                K.gemm(Qbuf[:, :cols], BSi, alpha=-1.0, beta=1.0, out=Yi_loc)
+            Yi = wrap(Yi_loc)
+            Qi, Ri = distla.qr(Yi)
+            Qi = project_out(Qi, Q)                                # Qi - Q (Q' Qi)
+            Qi, Rihat = distla.qr(Qi)
+            Ri = K.gemm(Rihat, Ri)
+            Bi = H[:, lo:hi].T.contiguous()
+            if cols > 0:
+                YtQ = distla.mm_t(Yi, Q)                           # b x cols
+                K.gemm(YtQ, Bc, alpha=-1.0, beta=1.0, out=Bi)
+                K.gemm(BSi, Bc, transa=True, alpha=-1.0, beta=1.0, out=Bi)
+            # Ri' X = Bi  (b x b triangular system with n right-hand sides: small dense glue)
+            Bi = torch.linalg.solve_triangular(Ri.T, Bi, upper=False)
+            Qbuf[:, cols:cols + (hi - lo)] = distla.local(Qi)
+            B[cols:cols + (hi - lo)] = Bi
+            cols += hi - lo
+            if use_tol:
+                sq_norm_A = sq_norm_A - float(K.sumsq(Bi.contiguous().reshape(-1)))
+                if sq_norm_A <= abs_sq_tol:
+                    break  # early stopping
+        return wrap(Qbuf[:, :cols]), B[:cols]
 
     exec = __call__

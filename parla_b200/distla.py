@@ -72,6 +72,22 @@ def orth(Y):
     return _like(K.gemm(Q1, Q2[rank * k:(rank + 1) * k].contiguous()), Y)
 
 
+def qr(Y):
+    """(Q, R) of a tall matrix (Householder; TSQR when row-sharded: R is replicated)."""
+    if not isinstance(Y, RowSharded):
+        return K.qr_economic(Y)
+    group = _group(Y)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    k = Y.local.shape[1]
+    if Y.local.shape[0] < k:
+        raise ValueError("TSQR needs at least as many local rows as columns on every rank")
+    Q1, R1 = K.qr_economic(Y.local)
+    stack = torch.empty(world * k, k, dtype=F64, device=R1.device)
+    dist.all_gather_into_tensor(stack, R1.contiguous(), group=group)
+    Q2, R2 = K.qr_economic(stack)
+    return _like(K.gemm(Q1, Q2[rank * k:(rank + 1) * k].contiguous()), Y), R2
+
+
 def local(X):
     return X.local if isinstance(X, RowSharded) else X
 

@@ -1,5 +1,8 @@
-"""Randomized eigendecomposition driver.  Mirrors parla/drivers/evd.py: interface (:171-208),
-``EVD1`` (:211-289; A symmetric)."""
+"""Randomized eigendecomposition drivers.  Mirrors parla/drivers/evd.py: interface (:171-208),
+``EVD1`` (:211-289; A symmetric) and ``EVD2`` (:290-381; A symmetric PSD, Nystrom)."""
+import math
+import warnings
+
 import numpy as np
 import torch
 import torch.distributed
@@ -47,6 +50,45 @@ class EVD1(EVDecomposer):
         U = U[:, I]
         lamb = lamb[I]
         V = distla.mm(Q, U.contiguous())                           # :288
+        return V, lamb
+
+    exec = __call__
+
+
+class EVD2(EVDecomposer):
+    """Rank-k truncation of the regularised Nystrom approximation (A S)(S'A S)^+ (A S)' of a symmetric PSD
+    matrix (evd.py:290-381; Tropp, Yurtsever, Udell, Cevher 2017, Algorithm 3)."""
+
+    TOL_CONTROL = 'none'
+
+    def __init__(self, sk_op):
+        self.sk_op = sk_op
+
+    def __call__(self, A, k, tol, over, rng):
+        assert k > 0                                               # evd.py:352-354
+        n = A.shape[0]
+        assert k < n
+        if not np.isnan(tol):
+            msg = """
+            This EVDecomposer implementation cannot directly control
+            approximation error. Parameter "tol" is being ignored.
+            """
+            warnings.warn(msg)
+        if isinstance(A, RowSharded):
+            raise NotImplementedError("EVD2 is implemented for a matrix resident on one GPU")
+        rng = np.random.default_rng(rng)
+        S = self.sk_op(A, k + over, rng).contiguous()              # n x (k + over)
+        Y = K.gemm(A, S)                                           # :363
+        nu = math.sqrt(n) * np.finfo(float).eps * math.sqrt(float(K.sumsq(Y.reshape(-1))))   # :365
+        Y.add_(S, alpha=nu)                                        # temporary regularisation (:367)
+        R = torch.linalg.cholesky(K.gemm(S, Y, transa=True), upper=True)      # small dense: cuSOLVER glue
+        Bm = K.gemm(Y, K.trtri_upper(R))                           # Y R^-1 = (R^-T Y')'   (:370)
+        Qb, Rb = K.qr_economic(Bm)                                 # thin SVD of the tall B through its QR
+        U, sigma, _ = torch.linalg.svd(Rb, full_matrices=False)
+        sig2 = (sigma * sigma).cpu().numpy()
+        r = min([k] + [i for i in range(k - 1) if sig2[i + 1] <= nu])          # :373-377
+        V = K.gemm(Qb, U[:, :r].contiguous())
+        lamb = (sigma * sigma)[:r] - nu
         return V, lamb
 
     exec = __call__

@@ -133,6 +133,25 @@ def srct_from_fixture(fx, d, m):
     return orc.SrctOperator((d, m), (fx["S_r"].astype(np.int64), e, fx["S_perm"].astype(np.int64)))
 
 
+QB3_FIXTURES = ["qb3_200x50", "qb3_tol_200x50", "qb3_wide_60x240"]
+EVD2_FIXTURES = ["evd2_120_over0", "evd2_120_over5", "evd2_120_exact"]
+
+
+def lowrank_matrix_from_fixture(fx):
+    """Test matrix of a QB3 / EVD2 fixture (oracle generators, hash-checked)."""
+    from oracle import parla_oracle as orc
+    rng = np.random.default_rng(int(fx["seed"]))
+    if str(fx["kind"]) == "evd2":
+        n, rank = int(fx["n"]), int(fx["rank"])
+        B0 = orc.rand_low_rank(n, rank, rank, rng)
+        A = B0 @ B0.T
+        A = 0.5 * (A + A.T)
+    else:
+        A = orc.exponent_spectrum(int(fx["m"]), int(fx["n"]), int(fx["rank"]), rng, 3.0)
+    assert digest(A) == str(fx["A_sha"])
+    return A
+
+
 class Replay:
     """sketch_op_gen that hands back a prerecorded operator (reference S replayed on the GPU path)."""
 

@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from oracle import parla_oracle as orc
-from tests.helpers import LOWRANK_FIXTURES, digest, load_golden
+from tests.helpers import (EVD2_FIXTURES, LOWRANK_FIXTURES, QB3_FIXTURES, digest, load_golden,
+                           lowrank_matrix_from_fixture)
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings("ignore")
@@ -131,3 +132,46 @@ def test_svd1_fixed_precision_and_evd_indefinite(rla):
     V, lam = rla.EVD1(rla.QB1(rla.RF1(rla.RS1(rla.SkOpGA(), 2, rla.orth, 1))))(dev(H), 5, np.nan, 5, 3)
     lam = lam.cpu().numpy()
     assert np.allclose(lam, [9, -8, 7, -6, 5], atol=1e-4) and V.shape == (150, 5)
+
+
+@pytest.mark.parametrize("name", QB3_FIXTURES + EVD2_FIXTURES)
+def test_qb3_evd2_match_reference_fixture(rla, name):
+    """QB3 (comps/qb.py:484-598) and EVD2 (drivers/evd.py:290-381), numpy Gaussian test matrices replayed."""
+    fx = load_golden(name)
+    A = lowrank_matrix_from_fixture(fx)
+    Ad = dev(A)
+    if str(fx["kind"]) == "qb3":
+        alg = rla.QB3(rla.RS1(orc.SkOpGA(), 0, rla.orth, 1), int(fx["blk"]))
+        Q, B = alg(Ad, int(fx["k"]), float(fx["tol"]), np.random.default_rng(7))
+        Q, B = Q.cpu().numpy(), B.cpu().numpy()
+        assert Q.shape[1] == int(fx["qb_cols"]) and B.shape == (Q.shape[1], A.shape[1])
+        assert np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])) < 1e-10              # test_valid_onb
+        assert np.linalg.norm(B - Q.T @ A) <= 1e-8 * np.linalg.norm(A)            # test_exact_B
+        approx = Q @ B
+    else:
+        alg = rla.EVD2(rla.RS1(orc.SkOpGA(), 1, rla.orth, 1))
+        V, lam = alg(Ad, int(fx["k"]), np.nan, int(fx["over"]), np.random.default_rng(7))
+        V, lam = V.cpu().numpy(), lam.cpu().numpy()
+        assert lam.shape == fx["spec"].shape and np.all(lam > 0)
+        assert np.max(np.abs(lam - fx["spec"])) <= 1e-9 * np.max(fx["spec"])
+        assert np.linalg.norm(V.T @ V - np.eye(V.shape[1])) < 1e-10
+        approx = (V * lam) @ V.T
+    assert torch.equal(Ad.cpu(), torch.from_numpy(A))                             # test_unchanged_A
+    sr, sc = max(1, A.shape[0] // 16), max(1, A.shape[1] // 16)
+    assert np.max(np.abs(approx[::sr, ::sc] - fx["approx_probe"])) <= 1e-9 * float(fx["approx_fro"])
+    assert abs(np.linalg.norm(A - approx) - float(fx["err_fro"])) <= 1e-9 * float(fx["approx_fro"])
+
+
+def test_qb3_evd2_interface_errors(rla):
+    A = torch.randn(40, 30, dtype=torch.float64, device="cuda")
+    with pytest.raises(AssertionError):
+        rla.QB3(rla.RS1(rla.SkOpGA(), 0, rla.orth, 1), 4)(A, 30, np.nan, 0)       # needs k < min(A.shape)
+    with pytest.raises(RuntimeError):
+        rla.QB3(lambda A_, k_, rng_: "not a matrix", 4)(A, 5, np.nan, 0)          # qb.py:568-574
+    H = A.T @ A
+    with pytest.raises(AssertionError):
+        rla.EVD2(rla.RS1(rla.SkOpGA(), 1, rla.orth, 1))(H, 30, np.nan, 0, 0)
+    with pytest.warns(UserWarning):
+        rla.EVD2(rla.RS1(rla.SkOpGA(), 1, rla.orth, 1))(H, 5, 1e-3, 2, 0)
+    Q, B = rla.QB3(rla.RS1(rla.SkOpGA(), 2, rla.orth, 1), 8)(A, 20, np.nan, 0)    # native operators
+    assert float(torch.linalg.norm(Q.T @ Q - torch.eye(20, dtype=torch.float64, device="cuda"))) < 1e-10
