@@ -5,9 +5,9 @@ Package-level names follow parla/__init__.py:8-19 for the components on the path
 __version__ = '0.1.0'
 
 from .utils.sketching import (gaussian_operator, sjlt_operator, srct_operator, generate_srct, apply_srct,
-                              as_device_operator)
+                              sparse_sign_operator, orthonormal_operator, sampling_operator, as_device_operator)
 from .utils.linalg_wrappers import orth
-from .comps.sketchers.oblivious import SkOpGA, SkOpSJ, SkOpTC, SketchOpGen
+from .comps.sketchers.oblivious import SkOpGA, SkOpSJ, SkOpTC, SkOpSS, SkOpON, SkOpIN, SketchOpGen
 from .comps.sketchers.aware import RS1, RowSketcher
 from .comps.qb import QB1, QB2, QB3, QBDecomposer
 from .comps.rangefinders import RF1, RangeFinder

@@ -44,3 +44,36 @@ class SkOpTC(SketchOpGen):
         return usk.srct_operator(n_rows, n_cols, rng)
 
     exec = __call__
+
+
+class SkOpON(SketchOpGen):
+    """Orthonormal operator generator (oblivious.py:31-35)."""
+
+    def __call__(self, n_rows, n_cols, rng):
+        return usk.orthonormal_operator(n_rows, n_cols, rng)
+
+    exec = __call__
+
+
+class SkOpSS(SketchOpGen):
+    """Sparse-sign operator generator (oblivious.py:58-65; the reference's __call__ forgets to return)."""
+
+    def __init__(self, density=0.05):
+        self.density = density
+
+    def __call__(self, n_rows, n_cols, rng):
+        return usk.sparse_sign_operator(n_rows, n_cols, rng, self.density)
+
+    exec = __call__
+
+
+class SkOpIN(SketchOpGen):
+    """Index (row / column sampling) operator generator (oblivious.py:75-82)."""
+
+    def __init__(self, indices=None):
+        self.indices = indices
+
+    def __call__(self, n_rows, n_cols, rng):
+        return usk.sampling_operator(n_rows, n_cols, rng, self.indices)
+
+    exec = __call__

@@ -487,3 +487,83 @@ def srct_operator(n_rows, n_cols, rng, device=None):
         return SRCTOperator(n_rows, n_cols, r, e, perm, device)
     wide = srct_operator(n_cols, n_rows, rng, device)
     return DenseOperator(wide.to_dense().T.contiguous())
+
+
+def orthonormal_operator(n_rows, n_cols, rng, device=None):
+    """parla/utils/sketching.py:9-17: the sign-normalised Q factor of a Gaussian matrix (orthonormal columns if
+    tall, orthonormal rows if wide), as a dense device operator."""
+    if n_rows < n_cols:
+        return DenseOperator(orthonormal_operator(n_cols, n_rows, rng, device).S.T.contiguous())
+    rng = np.random.default_rng(rng)
+    G = gaussian_operator(n_rows, n_cols, rng, device=device).to_dense()
+    Q, R = K.qr_economic(G)
+    return DenseOperator((Q * torch.sign(torch.diagonal(R))).contiguous())
+
+
+def sparse_sign_operator(n_rows, n_cols, rng, density=0.05, device=None):
+    """parla/utils/sketching.py:83-103: iid sparse sign matrix, each entry nonzero with probability ``density``,
+    values +-1/sqrt(min(n_rows, n_cols) * density).  Held densely on the device (applied with the DMMA GEMM)."""
+    seed, _ = _draw_key(rng)
+    device = _device(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    for attempt in range(11):
+        mask = torch.rand(n_rows, n_cols, generator=gen, device=device) < density
+        if bool(mask.any()):
+            break
+        if attempt == 10:
+            raise RuntimeError('Density too low.')
+    sign = torch.where(torch.rand(n_rows, n_cols, generator=gen, device=device) < 0.5, -1.0, 1.0).to(F64)
+    S = torch.where(mask, sign, torch.zeros((), dtype=F64, device=device)) / math.sqrt(min(n_rows, n_cols) * density)
+    return DenseOperator(S.contiguous())
+
+
+class SamplingOperator(SketchOperator):
+    """Row-sampling operator: (S @ A)[i] = A[indices[i]]  (parla/utils/sketching.py:204-236, wide form)."""
+
+    def __init__(self, n_rows, n_cols, indices):
+        self.shape = (int(n_rows), int(n_cols))
+        self.indices = indices
+
+    def sketch_into(self, A, b, out, row_offset=0):
+        n = A.shape[1]
+        if A.shape[0] != self.shape[1]:
+            raise ValueError("a sampling operator cannot be applied to a row shard")
+        K.gather_rows_scale(A, self.indices, None, 0, n, out[:, :n])
+        if b is not None:
+            out[:, n] = b[self.indices]
+        return out
+
+    def apply(self, A):
+        out = torch.empty(self.shape[0], A.shape[1], dtype=F64, device=A.device)
+        return self.sketch_into(A, None, out)
+
+    def to_dense(self):
+        S = torch.zeros(self.shape, dtype=F64, device=self.indices.device)
+        S[torch.arange(self.shape[0], device=self.indices.device), self.indices] = 1.0
+        return S
+
+    def rmatvec(self, v, m_local=None, row_offset=0):
+        out = torch.zeros(self.shape[1], dtype=F64, device=v.device)
+        out[self.indices] = v
+        return out
+
+
+def sampling_operator(n_rows, n_cols, rng, indices=None, device=None):
+    """parla/utils/sketching.py:204-236: keep ``min(n_rows, n_cols)`` sorted, distinct positions of the long axis
+    (drawn without replacement unless ``indices`` is given).  Wide: a SamplingOperator; tall: its transpose as a
+    dense device matrix."""
+    device = _device(device)
+    pop, size = max(n_rows, n_cols), min(n_rows, n_cols)
+    if indices is None:
+        seed, _ = _draw_key(rng)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed)
+        idx = torch.sort(torch.randperm(pop, generator=gen, device=device)[:size])[0]
+    else:
+        idx = torch.as_tensor(np.asarray(indices), device=device).to(torch.int64)
+        assert idx.numel() == size
+    S = SamplingOperator(size, pop, idx.contiguous())
+    if n_cols >= n_rows:
+        return S
+    return DenseOperator(S.to_dense().T.contiguous())

@@ -117,3 +117,38 @@ def test_srct_generation_and_tall_form(rla):
     fwd = rla.apply_srct(r, e, x, perm)
     back = rla.apply_srct(r, e, fwd, perm, forward=False)
     assert back.shape == (1000,) and fwd.shape == (40,)
+
+
+def test_orthonormal_sparse_sign_and_sampling_operators(rla):
+    """utils/sketching.py:9-17 (orthonormal), :83-103 (sparse sign), :204-236 (sampling) and their generators
+    SkOpON / SkOpSS / SkOpIN (oblivious.py:31-35,58-65,75-82), used as sketch_op_gen of SPO."""
+    eye = lambda k: torch.eye(k, dtype=torch.float64, device="cuda")
+    Q = rla.orthonormal_operator(300, 20, 3).to_dense()
+    assert Q.shape == (300, 20) and float(torch.linalg.norm(Q.T @ Q - eye(20))) < 1e-12
+    W = rla.orthonormal_operator(20, 300, 3).to_dense()
+    assert W.shape == (20, 300) and float(torch.linalg.norm(W @ W.T - eye(20))) < 1e-12
+    S = rla.sparse_sign_operator(50, 4000, 5, density=0.1).to_dense()
+    nz = S != 0
+    assert 0.08 < float(nz.double().mean()) < 0.12
+    assert torch.allclose(S[nz].abs(), torch.full_like(S[nz], 1 / np.sqrt(50 * 0.1)))
+    assert 0.4 < float((S[nz] > 0).double().mean()) < 0.6
+    with pytest.raises(RuntimeError):
+        rla.sparse_sign_operator(3, 3, 0, density=0.0)
+    A = torch.randn(4000, 9, dtype=torch.float64, device="cuda")
+    b = torch.randn(4000, dtype=torch.float64, device="cuda")
+    P = rla.sampling_operator(40, 4000, 7)
+    idx = P.indices
+    assert idx.numel() == 40 and bool((idx[1:] > idx[:-1]).all())
+    assert torch.equal(P @ A, A[idx]) and torch.equal(P @ b, b[idx])
+    assert torch.equal(P.to_dense() @ A, A[idx])
+    P2 = rla.SkOpIN(indices=np.arange(0, 4000, 100))(40, 4000, None)
+    assert torch.equal(P2 @ A, A[::100])
+    v = torch.randn(40, dtype=torch.float64, device="cuda")
+    assert torch.equal(P.rmatvec(v), P.to_dense().T @ v)
+    # as sketching operators of the least-squares driver
+    Awide = torch.randn(3000, 40, dtype=torch.float64, device="cuda")
+    bb = torch.randn(3000, dtype=torch.float64, device="cuda")
+    ref = torch.linalg.lstsq(Awide, bb.reshape(-1, 1)).solution.reshape(-1)
+    for gen in (rla.SkOpSS(0.05), rla.SkOpON(), rla.SkOpIN()):
+        x, log = rla.SPO(gen, 6, 'qr')(Awide, bb, 0.0, 1e-12, 200, 11)
+        assert float(torch.linalg.vector_norm(x - ref) / torch.linalg.vector_norm(ref)) < 1e-9

@@ -114,7 +114,8 @@ def test_row_sharded_allreduce_gloo_world2():
 
 def test_saddle_and_srct_public_names():
     for name in ("SPS1", "SPS2", "sps", "SaddleSolver", "PcSS1", "PcSS2", "pcss1", "pcss2", "pcg", "SPU1",
-                 "SkOpTC", "srct_operator", "generate_srct", "apply_srct"):
+                 "SkOpTC", "srct_operator", "generate_srct", "apply_srct", "QB3", "EVD2", "SkOpSS", "SkOpON", "SkOpIN",
+                 "sparse_sign_operator", "orthonormal_operator", "sampling_operator"):
         assert hasattr(rla, name), name
     for cls in (rla.SPS1, rla.SPS2, rla.PcSS1, rla.PcSS2, rla.SkOpTC, rla.SPU1):
         assert cls.exec is cls.__call__
