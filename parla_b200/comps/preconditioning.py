@@ -103,6 +103,16 @@ class PrecondOperator:
         return y
 
 
+def a_lift(A, scale):
+    """parla/comps/preconditioning.py:6-13: ``[A; scale * I]`` (A itself when scale == 0).  Provided for API
+    completeness -- it COPIES A; nothing on the solver path calls it (the ridge rows stay implicit)."""
+    if scale == 0:
+        return A
+    A = unwrap(A)[0]
+    n = A.shape[1]
+    return torch.cat((A, scale * torch.eye(n, dtype=A.dtype, device=A.device)), dim=0)
+
+
 def a_lift_precond(A, delta, R, upper_tri=False, k=1):
     """Signature of parla/comps/preconditioning.py:16.  Returns (A_precond, M_fwd, M_adj)."""
     if k != 1:

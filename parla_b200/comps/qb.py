@@ -17,6 +17,33 @@ from .rangefinders import RangeFinder
 F64 = torch.float64
 
 
+def _default_rs1(num_pass):
+    from .sketchers import oblivious
+    from .sketchers.aware import RS1
+    from ..utils import linalg_wrappers as ulaw
+    return RS1(oblivious.SkOpGA(), num_pass, ulaw.orth, 1)
+
+
+def qb(num_passes, A, k, rng):
+    """qb.py:16-82: RS1 (num_passes - 2 power-iteration passes) -> RF1 -> QB1."""
+    from .rangefinders import RF1
+    rng = np.random.default_rng(rng)
+    return QB1(RF1(_default_rs1(num_passes - 2)))(A, k, np.nan, rng)
+
+
+def qb_b(inner_num_pass, blk, overwrite_A, A, k, tol, rng):
+    """qb.py:85-167: blocked QB ([YGL:2018, Algorithm 2] up to the differences listed there)."""
+    from .rangefinders import RF1
+    rng = np.random.default_rng(rng)
+    return QB2(RF1(_default_rs1(inner_num_pass - 2)), blk, overwrite_A)(A, k, tol, rng)
+
+
+def qb_b_pe(num_passes, blk, A, k, tol, rng):
+    """qb.py:170-234: pass-efficient blocked QB (QB3)."""
+    rng = np.random.default_rng(rng)
+    return QB3(_default_rs1(num_passes - 1), blk)(A, k, tol, rng)
+
+
 class QBDecomposer:
 
     def __call__(self, A, k, tol, rng):

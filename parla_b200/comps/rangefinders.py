@@ -7,6 +7,16 @@ from .. import distla
 from .sketchers.aware import RowSketcher
 
 
+def rf1(A, k, num_pass, rng):
+    """rangefinders.py:22-71: RS1 (Gaussian, num_pass - 1 power-iteration passes) -> RF1."""
+    from .sketchers import oblivious
+    from .sketchers.aware import RS1
+    from ..utils import linalg_wrappers as ulaw
+    rng = np.random.default_rng(rng)
+    rso_ = RS1(sketch_op_gen=oblivious.SkOpGA(), num_pass=num_pass - 1, stabilizer=ulaw.orth, passes_per_stab=1)
+    return RF1(rso_)(A, k, 0.0, rng)      # (:70 passes tol = 0.0, which RF1 reports as ignored)
+
+
 class RangeFinder:
 
     def __call__(self, A, k, tol, rng):

@@ -28,11 +28,16 @@ def _tall_test_matrix(gen, A, k, rng):
     return RowSharded(loc, A.row_offset, A.m_global, A.group)
 
 
-def rs1(A, k, num_pass, rng, stabilizer, passes_per_stab=1, sketch_op_gen=None):
-    """Procedural wrapper (aware.py:9-30)."""
+def rs1(A, k, num_pass, rng, stabilizer=None, passes_per_stab=1, sketch_op_gen=None):
+    """Procedural wrapper (aware.py:9-30): Gaussian start, ``num_pass`` power-iteration passes, QR-stabilised
+    after every pass.  (The extra keyword arguments are conveniences of this package.)"""
     from . import oblivious
+    from ...utils import linalg_wrappers as ulaw
+    assert num_pass >= 0
+    assert k >= 1
+    assert k <= min(A.shape)
     gen = oblivious.SkOpGA() if sketch_op_gen is None else sketch_op_gen
-    return RS1(gen, num_pass, stabilizer, passes_per_stab)(A, k, rng)
+    return RS1(gen, num_pass, ulaw.orth if stabilizer is None else stabilizer, passes_per_stab)(A, k, rng)
 
 
 class RowSketcher:

@@ -13,6 +13,29 @@ from ..parallel import RowSharded, allreduce_
 from ..comps.qb import QBDecomposer
 
 
+def evd1(A, k, tol, over, inner_num_pass, block_size, rng):
+    """evd.py:16-96 (note: tol is halved here and again inside EVD1, as in the reference)."""
+    from ..comps.sketchers import oblivious
+    from ..comps.sketchers.aware import RS1
+    from ..comps.rangefinders import RF1
+    from ..comps.qb import QB2
+    from ..utils import linalg_wrappers as ulaw
+    assert inner_num_pass >= 2
+    rng = np.random.default_rng(rng)
+    rso_ = RS1(oblivious.SkOpGA(), inner_num_pass - 2, ulaw.orth, 1)
+    return EVD1(QB2(RF1(rso_), block_size, overwrite_a=False))(A, k, tol / 2, over, rng)
+
+
+def evd2(A, k, over, num_passes, rng):
+    """evd.py:99-164."""
+    from ..comps.sketchers import oblivious
+    from ..comps.sketchers.aware import RS1
+    from ..utils import linalg_wrappers as ulaw
+    assert num_passes >= 1
+    rng = np.random.default_rng(rng)
+    return EVD2(RS1(oblivious.SkOpGA(), num_passes - 1, ulaw.orth, 1))(A, k, np.nan, over, rng)
+
+
 class EVDecomposer:
 
     def __call__(self, A, k, tol, over, rng):

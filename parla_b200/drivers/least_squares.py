@@ -108,6 +108,13 @@ def _sketch(sketch_op_gen, d, A, b, delta, rng):
     return S, W
 
 
+def sso1(A, b, delta, rng, sampling_factor=3, vec_nnz=8, lapack_driver='gelsd'):
+    """least_squares.py:108-111."""
+    from ..comps.sketchers import oblivious as sko
+    alg = SSO1(sko.SkOpSJ(vec_nnz), sampling_factor, lapack_driver, overwrite_sketch=True)
+    return alg(A, b, delta, np.nan, 1, rng, logging=True)
+
+
 class SSO1(OverLstsqSolver):
     """Sketch-and-solve (least_squares.py:114-189): x = argmin ||S A x - S b||, via Householder QR."""
 
@@ -153,6 +160,18 @@ def _clock(logging):
         torch.cuda.synchronize()
         return time.time()
     return now
+
+
+def spo1(A, b, delta, tol, iter_lim, rng, sampling_factor=3, vec_nnz=8):
+    """least_squares.py:193-196 (SVD preconditioner)."""
+    from ..comps.sketchers import oblivious as sko
+    return SPO(sko.SkOpSJ(vec_nnz), sampling_factor, mode='svd')(A, b, delta, tol, iter_lim, rng, logging=True)
+
+
+def spo3(A, b, delta, tol, iter_lim, rng, sampling_factor=3, vec_nnz=8, mode='qr'):
+    """least_squares.py:200-203."""
+    from ..comps.sketchers import oblivious as sko
+    return SPO(sko.SkOpSJ(vec_nnz), sampling_factor, mode)(A, b, delta, tol, iter_lim, rng, logging=True)
 
 
 class SPO(OverLstsqSolver):
@@ -276,6 +295,12 @@ class UnderLstsqSolver:
         raise NotImplementedError()
 
     exec = __call__
+
+
+def spu1(A, c, tol, iter_lim, rng, sampling_factor=3, vec_nnz=8):
+    """least_squares.py:419-422."""
+    from ..comps.sketchers import oblivious as sko
+    return SPU1(sko.SkOpSJ(vec_nnz), sampling_factor)(A, c, tol, iter_lim, rng, logging=True)
 
 
 class SPU1(UnderLstsqSolver):

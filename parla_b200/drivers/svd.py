@@ -6,6 +6,19 @@ from .. import distla
 from ..comps.qb import QBDecomposer
 
 
+def svd1(A, k, over, tol, inner_num_pass, block_size, rng):
+    """svd.py:58-123: RS1 (Gaussian, inner_num_pass - 2 power-iteration passes, QR-stabilised) -> RF1 ->
+    QB2(block_size) -> SVD1."""
+    from ..comps.sketchers import oblivious
+    from ..comps.sketchers.aware import RS1
+    from ..comps.rangefinders import RF1
+    from ..comps.qb import QB2
+    from ..utils import linalg_wrappers as ulaw
+    rng = np.random.default_rng(rng)
+    rso_ = RS1(oblivious.SkOpGA(), inner_num_pass - 2, ulaw.orth, 1)
+    return SVD1(QB2(RF1(rso_), block_size, overwrite_a=False))(A, k, tol, over, rng)
+
+
 class SVDecomposer:
 
     def __call__(self, A, k, tol, over, rng):

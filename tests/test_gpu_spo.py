@@ -267,3 +267,50 @@ def test_svd_right_precond_gram_route_and_fallback(rla):
     assert float(torch.linalg.vector_norm(x_svd - x_qr) / torch.linalg.vector_norm(x_qr)) <= 1e-10
     assert abs(log_svd.iters - log_qr.iters) <= 1
     assert np.allclose(log_svd.errors[:10], log_qr.errors[:10], rtol=1e-6)      # |M'A'r| is rotation invariant
+
+
+def test_procedural_wrappers_run(rla):
+    """sso1 / spo1 / spo3 / spu1 / sps (least_squares.py:108,193,200,419; saddlesys.py:77), svd1 / evd1 / evd2
+    (svd.py:58, evd.py:16,99), qb / qb_b / qb_b_pe / rf1 / rs1 (qb.py:16,85,170; rangefinders.py:22; aware.py:9)
+    and the small linear-algebra helpers of utils/linalg_wrappers.py."""
+    from parla_b200.drivers import least_squares as ls, svd as dsvd, evd as devd
+    from parla_b200.comps import qb as cqb, rangefinders as crf, preconditioning as cpc
+    from parla_b200.comps.sketchers import aware
+    from parla_b200.utils import linalg_wrappers as ulaw
+    g = torch.Generator(device="cuda").manual_seed(9)
+    rn = lambda *s: torch.randn(*s, dtype=torch.float64, device="cuda", generator=g)
+    A, b, c = rn(2000, 30), rn(2000), rn(30)
+    x_ls = torch.linalg.lstsq(A, b.reshape(-1, 1)).solution.reshape(-1)
+    close = lambda x, y, t: float(torch.linalg.vector_norm(x - y) / torch.linalg.vector_norm(y)) <= t
+    assert close(ls.spo1(A, b, 0.0, 1e-12, 100, 1)[0], x_ls, 1e-9)
+    assert close(ls.spo3(A, b, 0.0, 1e-12, 100, 1, mode='chol')[0], x_ls, 1e-9)
+    b_sig = A @ rn(30) + 0.01 * rn(2000)                          # small residual: sketch-and-solve is then accurate
+    x_sig = torch.linalg.lstsq(A, b_sig.reshape(-1, 1)).solution.reshape(-1)
+    assert close(ls.sso1(A, b_sig, 0.0, 1, sampling_factor=20)[0], x_sig, 1e-2)
+    y, _ = ls.spu1(A, c, 1e-12, 100, 1)
+    assert close(A.T @ y, c, 1e-9)
+    x, yy, _ = rla.sps(A, b, c, 0.3, 1e-12, 100, 1, method='pcg')
+    G = A.T @ A + 0.3 * torch.eye(30, dtype=torch.float64, device="cuda")
+    assert close(x, torch.linalg.solve(G, A.T @ b - c), 1e-8)
+    L = rn(400, 12) @ rn(12, 90)                                   # exact rank 12
+    U, s, Vh = dsvd.svd1(L, 12, 4, 0.0, 2, 8, 3)
+    assert close((U * s) @ Vh, L, 1e-10)
+    for Q, B in (cqb.qb(2, L, 12, 3), cqb.qb_b(2, 4, False, L, 12, 0.0, 3), cqb.qb_b_pe(1, 4, L, 12, np.nan, 3)):
+        assert close(Q @ B, L, 1e-9)
+    assert crf.rf1(L, 12, 1, 3).shape == (400, 12) and aware.rs1(L, 12, 2, 3).shape == (90, 12)
+    H = L.T @ L
+    V, lam = devd.evd1(H, 12, 0.0, 4, 2, 8, 3)
+    assert close((V * lam) @ V.T, H, 1e-9)
+    V, lam = devd.evd2(H, 8, 3, 2, 3)
+    assert V.shape == (90, 8) and bool((lam > 0).all())
+    assert cpc.a_lift(A, 0.0) is A and cpc.a_lift(A, 2.0).shape == (2030, 30)
+    M = rn(40, 25)
+    Lf, Uf, P = ulaw.lupt(M)
+    assert close(Lf @ Uf @ P.T, M, 1e-12)
+    Lf, Uf, P = ulaw.lup(M)
+    assert close(Lf @ Uf @ P, M, 1e-12)
+    assert ulaw.lu_stabilize(M).shape == (40, 25)
+    T = rn(40, 6)
+    assert close(M @ ulaw.apply_pinv_on_left(T, M), M @ torch.linalg.pinv(M) @ T, 1e-9)
+    Mw, Tr = rn(25, 40), rn(6, 40)                                 # wide operator: target @ pinv(operator) is 6 x 25
+    assert close(ulaw.apply_pinv_on_right(Tr, Mw), Tr @ torch.linalg.pinv(Mw), 1e-9)

@@ -143,3 +143,46 @@ def test_srct_two_level_plan_choice():
     m2 = 8
     kk = np.arange(m2 + 1)[:, None] * np.arange(m2)[None, :]
     assert np.allclose(np.cos(np.pi * (kk % (2 * m2)) / m2), np.cos(np.pi * kk / m2), atol=1e-15)
+
+
+def test_procedural_wrappers_and_utils_exist():
+    """Every module-level function of the reference's drivers/comps/utils has a counterpart with the same
+    positional signature (parla/drivers/*.py, comps/*.py, utils/*.py)."""
+    import inspect
+    from parla_b200.drivers import least_squares as ls, svd as dsvd, evd as devd, saddlesys as dss
+    from parla_b200.comps import qb as cqb, rangefinders as crf, preconditioning as cpc
+    from parla_b200.comps.sketchers import aware
+    from parla_b200.comps.determiter import saddle as dsad
+    from parla_b200.utils import linalg_wrappers as ulaw, stats as ustats, misc
+    want = {ls.sso1: ["A", "b", "delta", "rng", "sampling_factor", "vec_nnz", "lapack_driver"],
+            ls.spo1: ["A", "b", "delta", "tol", "iter_lim", "rng", "sampling_factor", "vec_nnz"],
+            ls.spo3: ["A", "b", "delta", "tol", "iter_lim", "rng", "sampling_factor", "vec_nnz", "mode"],
+            ls.spu1: ["A", "c", "tol", "iter_lim", "rng", "sampling_factor", "vec_nnz"],
+            dss.sps: ["A", "b", "c", "delta", "tol", "iter_lim", "rng", "sampling_factor", "vec_nnz", "method"],
+            dsvd.svd1: ["A", "k", "over", "tol", "inner_num_pass", "block_size", "rng"],
+            devd.evd1: ["A", "k", "tol", "over", "inner_num_pass", "block_size", "rng"],
+            devd.evd2: ["A", "k", "over", "num_passes", "rng"],
+            cqb.qb: ["num_passes", "A", "k", "rng"],
+            cqb.qb_b: ["inner_num_pass", "blk", "overwrite_A", "A", "k", "tol", "rng"],
+            cqb.qb_b_pe: ["num_passes", "blk", "A", "k", "tol", "rng"],
+            crf.rf1: ["A", "k", "num_pass", "rng"],
+            dsad.pcss1: ["A", "b", "c", "delta", "tol", "iter_lim", "R", "upper_tri", "z0"],
+            dsad.pcss2: ["A", "b", "c", "delta", "tol", "iter_lim", "R", "upper_tri", "z0"],
+            cpc.a_lift: ["A", "scale"], cpc.a_lift_precond: ["A", "delta", "R", "upper_tri", "k"]}
+    for fn, names in want.items():
+        assert list(inspect.signature(fn).parameters)[:len(names)] == names, fn.__name__
+    assert list(inspect.signature(aware.rs1).parameters)[:4] == ["A", "k", "num_pass", "rng"]
+    for name in ("orth", "lu_stabilize", "lupt", "lup", "apply_pinv_on_left", "apply_pinv_on_right"):
+        assert callable(getattr(ulaw, name))
+    t = np.arange(30.0)
+    fit, r2 = ustats.loglinear_fit(t, 3.0 * np.exp(-0.7 * t))
+    assert np.allclose(fit, [np.log(3.0), -0.7]) and r2 > 1 - 1e-12
+    fit, r2 = ustats.loglog_fit(t + 1, 2.0 * (t + 1) ** -1.5)
+    assert np.allclose(fit, [np.log(2.0), -1.5]) and r2 > 1 - 1e-12
+    with pytest.raises(ValueError):
+        ustats.loglog_fit(t, t + 1)
+
+    @misc.set_docstring("hello")
+    def f():
+        pass
+    assert f.__doc__ == "hello"
