@@ -297,6 +297,47 @@ def qb3_evd2_cases():
                             approx_probe=ap[::max(1, n // 16), ::max(1, n // 16)])
 
 
+def id_cases():
+    """Interpolative / CUR decompositions (drivers/interpolative.py; test_osid.py, test_tsid.py, test_cur.py)."""
+    import parla.drivers.interpolative as rid
+    import parla.comps.interpolative as rci
+    import parla.comps.sketchers.aware as raw
+    for name, m, n, rank, k, over, npass, seed in (("id_tall_100x30", 100, 30, 30, 25, 4, 2, 51),
+                                                   ("id_wide_30x100", 30, 100, 30, 27, 3, 2, 52),
+                                                   ("id_exact_100x30", 100, 30, 5, 5, 1, 0, 53),
+                                                   ("id_big_2000x300", 2000, 300, 120, 40, 10, 1, 54)):
+        A = orc.rand_low_rank(m, n, rank, np.random.default_rng(seed))
+        assert relerr(A, rmm.rand_low_rank(m, n, rank, np.random.default_rng(seed))) < 1e-13
+        rs_r, rs_o = raw.RS1(rsko.SkOpGA(), npass, rulaw.orth, 1), orc.RS1(orc.SkOpGA(), npass, orc.orth, 1)
+        fx = dict(m=m, n=n, rank=rank, k=k, over=over, num_pass=npass, seed=seed, A_sha=digest(A),
+                  A_fro=np.linalg.norm(A))
+        for axis in (0, 1):
+            for tag, R_, O_ in (("osid1", rid.OSID1, orc.OSID1), ("osid2", rid.OSID2, orc.OSID2)):
+                Mr, Pr = R_(rs_r)(A, k, over, axis, np.random.default_rng(7))
+                Mo, Po = O_(rs_o)(A, k, over, axis, np.random.default_rng(7))
+                assert np.array_equal(Pr, Po) and relerr(Mo, Mr) < 1e-8
+                approx = Mr @ A[Pr, :] if axis == 0 else A[:, Pr] @ Mr
+                fx[f"{tag}_ax{axis}_idx"] = Pr.astype(np.int32)
+                fx[f"{tag}_ax{axis}_err"] = np.linalg.norm(A - approx)
+            Pr = rci.ROCS1(rs_r)(A, k, over, axis, np.random.default_rng(7))
+            assert np.array_equal(Pr, orc.ROCS1(rs_o)(A, k, over, axis, np.random.default_rng(7)))
+            fx[f"rocs1_ax{axis}_idx"] = Pr.astype(np.int32)
+        Z, Is, X, Js = rid.TSID1(rid.OSID1(rs_r))(A, k, over, np.random.default_rng(7))
+        Zo, Iso, Xo, Jso = orc.TSID1(orc.OSID1(rs_o))(A, k, over, np.random.default_rng(7))
+        assert np.array_equal(Is, Iso) and np.array_equal(Js, Jso) and relerr(Zo, Z) < 1e-8 and relerr(Xo, X) < 1e-8
+        fx.update(tsid_Is=Is.astype(np.int32), tsid_Js=Js.astype(np.int32),
+                  tsid_err=np.linalg.norm(A - Z @ A[Is, :][:, Js] @ X))
+        Js, U, Is = rid.CUR1(rid.OSID1(rs_r))(A, k, over, np.random.default_rng(7))
+        Jso, Uo, Iso = orc.CUR1(orc.OSID1(rs_o))(A, k, over, np.random.default_rng(7))
+        assert np.array_equal(Is, Iso) and np.array_equal(Js, Jso)
+        cur = A[:, Js] @ (U @ A[Is, :])
+        assert relerr(A[:, Js] @ (Uo @ A[Is, :]), cur) < 1e-8
+        fx.update(cur_Is=Is.astype(np.int32), cur_Js=Js.astype(np.int32), cur_err=np.linalg.norm(A - cur))
+        print(f"{name:28s} OSID1 row/col err {fx['osid1_ax0_err'] / fx['A_fro']:.2e}/{fx['osid1_ax1_err'] / fx['A_fro']:.2e}  "
+              f"TSID {fx['tsid_err'] / fx['A_fro']:.2e}  CUR {fx['cur_err'] / fx['A_fro']:.2e}")
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+
+
 def philox_case():
     """Known-answer vectors for Philox4x32-10 (Random123 kat_vectors) + oracle stream samples."""
     from oracle import philox_ref as ph
@@ -315,6 +356,9 @@ def philox_case():
 
 
 if __name__ == "__main__":
+    if "--only-id" in sys.argv:
+        id_cases()
+        sys.exit(0)
     if "--only-qb3" in sys.argv:
         qb3_evd2_cases()
         sys.exit(0)
@@ -351,4 +395,5 @@ if __name__ == "__main__":
     sps_cases()
     srct_cases()
     qb3_evd2_cases()
+    id_cases()
     print("golden fixtures written to", OUT)

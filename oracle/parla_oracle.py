@@ -560,6 +560,112 @@ class SPO:
 
 
 # ------------------------------------------------------------------------------------------
+#  Interpolative decompositions    (reference: comps/interpolative.py, drivers/interpolative.py)
+# ------------------------------------------------------------------------------------------
+
+def qrcp_osid(Y, k, axis):
+    """Rank-k one-sided ID of Y from a column-pivoted QR, comps/interpolative.py:11-67.
+    axis=1: (X, Js) with Y ~ Y[:, Js] X, X[:, Js] = I.  axis=0: (Z, Is) with Y ~ Z Y[Is, :]."""
+    if axis == 0:
+        X, Is = qrcp_osid(Y.T, k, 1)
+        return X.T, Is
+    if axis != 1:
+        raise ValueError()
+    _, R, J = sla.qr(Y, mode='economic', pivoting=True)
+    T = sla.solve_triangular(R[:k, :k], R[:k, k:], lower=False)
+    X = np.zeros((k, Y.shape[1]))
+    X[:, J] = np.hstack((np.eye(k), T))
+    return X, J[:k]
+
+
+def _pivots(Y, k):
+    return sla.qr(Y, mode='economic', pivoting=True)[2][:k]
+
+
+class ROCS1:
+    """Row / column selection: QRCP pivots of a sketch, comps/interpolative.py:131-157."""
+
+    def __init__(self, sk_op):
+        self.sk_op = sk_op
+
+    def __call__(self, A, k, over, axis, rng):
+        rng = np.random.default_rng(rng)
+        if axis == 0:
+            return _pivots((A @ self.sk_op(A, k + over, rng)).T, k)
+        if axis == 1:
+            return _pivots(self.sk_op(A.T, k + over, rng).T @ A, k)
+        raise ValueError()
+
+
+class OSID1:
+    """Sketch, then ID of the sketch, drivers/interpolative.py:97-134."""
+
+    def __init__(self, sk_op):
+        self.sk_op = sk_op
+
+    def __call__(self, A, k, over, axis, rng):
+        rng = np.random.default_rng(rng)
+        if axis == 0:
+            return qrcp_osid(A @ self.sk_op(A, k + over, rng), k, 0)
+        if axis == 1:
+            return qrcp_osid(self.sk_op(A.T, k + over, rng).T @ A, k, 1)
+        raise ValueError()
+
+
+class OSID2:
+    """Skeleton from the QRCP of a sketch, coefficients by a pseudo-inverse, drivers/interpolative.py:146-176."""
+
+    def __init__(self, sk_op):
+        self.sk_op = sk_op
+
+    def __call__(self, A, k, over, axis, rng):
+        rng = np.random.default_rng(rng)
+        if axis == 0:
+            Is = _pivots((A @ self.sk_op(A, k + over, rng)).T, k)
+            return sla.lstsq(A[Is, :].T, A.T)[0].T, Is              # A pinv(A[Is, :])
+        if axis == 1:
+            Js = _pivots(self.sk_op(A.T, k + over, rng).T @ A, k)
+            return sla.lstsq(A[:, Js], A)[0], Js                    # pinv(A[:, Js]) A
+        raise ValueError()
+
+
+class TSID1:
+    """Two-sided ID A ~ Z A[Is, Js] X, drivers/interpolative.py:257-278."""
+
+    def __init__(self, osid):
+        self.osid = osid
+
+    def __call__(self, A, k, over, rng):
+        rng = np.random.default_rng(rng)
+        if A.shape[0] > A.shape[1]:
+            X, Js = self.osid(A, k, over, axis=1, rng=rng)
+            Z, Is = qrcp_osid(A[:, Js], k, 0)
+        else:
+            Z, Is = self.osid(A, k, over, axis=0, rng=rng)
+            X, Js = qrcp_osid(A[Is, :], k, 1)
+        return Z, Is, X, Js
+
+
+class CUR1:
+    """CUR decomposition A ~ A[:, Js] U A[Is, :], drivers/interpolative.py:358-387."""
+
+    def __init__(self, osid):
+        self.osid = osid
+
+    def __call__(self, A, k, over, rng):
+        rng = np.random.default_rng(rng)
+        if A.shape[0] > A.shape[1]:
+            X, Js = self.osid(A, k, over, axis=1, rng=rng)
+            Is = _pivots(A[:, Js].T, k)
+            U = sla.lstsq(A[Is, :].T, X.T)[0].T                     # X pinv(A[Is, :])
+        else:
+            Z, Is = self.osid(A, k, over, axis=0, rng=rng)
+            Js = _pivots(A[Is, :], k)
+            U = sla.lstsq(A[:, Js], Z)[0]                           # pinv(A[:, Js]) Z
+        return Js, U, Is
+
+
+# ------------------------------------------------------------------------------------------
 #  Saddle-point systems            (reference: comps/determiter/pcg.py, comps/determiter/saddle.py:88-176,
 #                                   drivers/saddlesys.py:89-327)
 # ------------------------------------------------------------------------------------------

@@ -19,3 +19,5 @@ from .drivers.saddlesys import SPS1, SPS2, SaddleSolver, sps
 from .drivers.svd import SVD1, SVDecomposer
 from .drivers.evd import EVD1, EVD2, EVDecomposer
 from .parallel import RowSharded
+from .comps.interpolative import ROCS1, RowOrColSelection, qrcp_osid
+from .drivers.interpolative import OSID1, OSID2, OneSidedID, TSID1, TwoSidedID, CUR1, CURDecomposition

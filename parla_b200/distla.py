@@ -23,10 +23,19 @@ def _group(X):
     return X.group if X.group is not None else dist.group.WORLD
 
 
+def _is_transposed_view(A):
+    """True for ``B.T`` of a row-major B (column-major strides): its products are issued on B with the
+    transpose flag instead of materialising the transpose."""
+    return (isinstance(A, torch.Tensor) and A.dim() == 2 and A.shape[0] > 1 and A.shape[1] > 1
+            and A.stride(0) == 1 and A.stride(1) >= A.shape[0])
+
+
 def mm(A, S, alpha=1.0):
     """A @ S with S replicated.  Row-sharded A gives a row-sharded result."""
     if isinstance(A, RowSharded):
         return _like(K.gemm(A.local, S, alpha=alpha), A)
+    if _is_transposed_view(A):
+        return K.gemm(A.T, S, transa=True, alpha=alpha)
     return K.gemm(A, S, alpha=alpha)
 
 
@@ -37,6 +46,8 @@ def mm_t(A, Y, out=None):
             raise ValueError("A^T @ Y needs both operands sharded over the same rows")
         Z = K.gemm(A.local, Y.local, transa=True, out=out)
         return allreduce_(Z, _group(A))
+    if _is_transposed_view(A):
+        return K.gemm(A.T, Y, out=out)                 # (B')' Y = B Y
     return K.gemm(A, Y, transa=True, out=out)
 
 

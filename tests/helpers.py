@@ -152,6 +152,40 @@ def lowrank_matrix_from_fixture(fx):
     return A
 
 
+ID_FIXTURES = ["id_tall_100x30", "id_wide_30x100", "id_exact_100x30", "id_big_2000x300"]
+
+
+def check_id_fixture(fx, A, lib, sk_op, to_np, wrap):
+    """Run OSID1 / OSID2 / ROCS1 / TSID1 / CUR1 of ``lib`` (the oracle or parla_b200) on A and compare skeleton
+    indices (exactly) and approximation errors (1e-8 relative to |A|) with a fixture of reference outputs."""
+    k, over, fro = int(fx["k"]), int(fx["over"]), float(fx["A_fro"])
+    Aw = wrap(A)
+    for axis in (0, 1):
+        for tag, cls in (("osid1", lib.OSID1), ("osid2", lib.OSID2)):
+            M, P = cls(sk_op)(Aw, k, over, axis, np.random.default_rng(7))
+            M, P = to_np(M), to_np(P)
+            assert np.array_equal(P, fx[f"{tag}_ax{axis}_idx"]), (tag, axis)
+            approx = M @ A[P, :] if axis == 0 else A[:, P] @ M
+            assert abs(np.linalg.norm(A - approx) - float(fx[f"{tag}_ax{axis}_err"])) <= 1e-8 * fro
+            sub = M[P, :] if axis == 0 else M[:, P]
+            assert np.linalg.norm(sub - np.eye(k)) < 1e-8
+        assert np.array_equal(to_np(lib.ROCS1(sk_op)(Aw, k, over, axis, np.random.default_rng(7))),
+                              fx[f"rocs1_ax{axis}_idx"])
+    Z, Is, X, Js = (to_np(v) for v in lib.TSID1(lib.OSID1(sk_op))(Aw, k, over, np.random.default_rng(7)))
+    assert np.array_equal(Is, fx["tsid_Is"]) and np.array_equal(Js, fx["tsid_Js"])
+    assert abs(np.linalg.norm(A - Z @ A[Is, :][:, Js] @ X) - float(fx["tsid_err"])) <= 1e-8 * fro
+    Js, U, Is = (to_np(v) for v in lib.CUR1(lib.OSID1(sk_op))(Aw, k, over, np.random.default_rng(7)))
+    assert np.array_equal(Is, fx["cur_Is"]) and np.array_equal(Js, fx["cur_Js"])
+    assert abs(np.linalg.norm(A - A[:, Js] @ (U @ A[Is, :])) - float(fx["cur_err"])) <= 1e-8 * fro
+
+
+def id_matrix_from_fixture(fx):
+    from oracle import parla_oracle as orc
+    A = orc.rand_low_rank(int(fx["m"]), int(fx["n"]), int(fx["rank"]), np.random.default_rng(int(fx["seed"])))
+    assert digest(A) == str(fx["A_sha"])
+    return A
+
+
 class Replay:
     """sketch_op_gen that hands back a prerecorded operator (reference S replayed on the GPU path)."""
 

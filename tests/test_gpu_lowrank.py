@@ -8,8 +8,8 @@ import pytest
 import torch
 
 from oracle import parla_oracle as orc
-from tests.helpers import (EVD2_FIXTURES, LOWRANK_FIXTURES, QB3_FIXTURES, digest, load_golden,
-                           lowrank_matrix_from_fixture)
+from tests.helpers import (EVD2_FIXTURES, ID_FIXTURES, LOWRANK_FIXTURES, QB3_FIXTURES, check_id_fixture, digest,
+                           id_matrix_from_fixture, load_golden, lowrank_matrix_from_fixture)
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings("ignore")
@@ -175,3 +175,32 @@ def test_qb3_evd2_interface_errors(rla):
         rla.EVD2(rla.RS1(rla.SkOpGA(), 1, rla.orth, 1))(H, 5, 1e-3, 2, 0)
     Q, B = rla.QB3(rla.RS1(rla.SkOpGA(), 2, rla.orth, 1), 8)(A, 20, np.nan, 0)    # native operators
     assert float(torch.linalg.norm(Q.T @ Q - torch.eye(20, dtype=torch.float64, device="cuda"))) < 1e-10
+
+
+@pytest.mark.parametrize("name", ID_FIXTURES)
+def test_interpolative_matches_reference_fixture(rla, name):
+    """OSID1 / OSID2 / ROCS1 / TSID1 / CUR1 on the device (numpy Gaussian test matrices replayed): skeleton indices
+    equal to the reference's, approximation errors equal to 1e-8 |A|."""
+    import types
+    fx = load_golden(name)
+    A = id_matrix_from_fixture(fx)
+    sk_op = rla.RS1(orc.SkOpGA(), int(fx["num_pass"]), rla.orth, 1)
+    lib = types.SimpleNamespace(OSID1=rla.OSID1, OSID2=rla.OSID2, ROCS1=rla.ROCS1, TSID1=rla.TSID1, CUR1=rla.CUR1)
+    check_id_fixture(fx, A, lib, sk_op, lambda t: t.cpu().numpy(), dev)
+
+
+def test_interpolative_procedural_and_errors(rla):
+    from parla_b200.drivers import interpolative as did
+    from parla_b200.comps import interpolative as cid
+    A = torch.randn(300, 12, dtype=torch.float64, device="cuda") @ torch.randn(12, 80, dtype=torch.float64, device="cuda")
+    Z, Is = did.osid1(A, 12, 3, 2, 0, 1)
+    assert float(torch.linalg.norm(Z @ A[Is, :] - A) / torch.linalg.norm(A)) < 1e-10
+    X, Js = did.osid2(A, 12, 3, 1, 1, 1)
+    assert float(torch.linalg.norm(A[:, Js] @ X - A) / torch.linalg.norm(A)) < 1e-10
+    Z, Is, X, Js = did.tsid1(A, 12, 3, 2, 1)
+    assert float(torch.linalg.norm(Z @ A[Is, :][:, Js] @ X - A) / torch.linalg.norm(A)) < 1e-9
+    Js, U, Is = did.cur1(A, 12, 3, 2, 1)
+    assert float(torch.linalg.norm(A[:, Js] @ (U @ A[Is, :]) - A) / torch.linalg.norm(A)) < 1e-9
+    assert cid.rocs1(A, 12, 3, 2, 0, 1).numel() == 12
+    with pytest.raises(ValueError):
+        did.OSID1(rla.RS1(rla.SkOpGA(), 0, rla.orth, 1))(A, 5, 2, 2, 0)
