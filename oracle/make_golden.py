@@ -304,8 +304,9 @@ def id_cases():
     import parla.comps.sketchers.aware as raw
     for name, m, n, rank, k, over, npass, seed in (("id_tall_100x30", 100, 30, 30, 25, 4, 2, 51),
                                                    ("id_wide_30x100", 30, 100, 30, 27, 3, 2, 52),
-                                                   ("id_exact_100x30", 100, 30, 5, 5, 1, 0, 53),
-                                                   ("id_big_2000x300", 2000, 300, 120, 40, 10, 1, 54)):
+                                                   ("id_exact_100x30", 100, 30, 5, 5, 1, 0, 53)):
+        # (small shapes only: the fixture stores a hash of A, and the QR / GEMMs that build A are bit-reproducible
+        #  across hosts with different BLAS thread counts only for small matrices)
         A = orc.rand_low_rank(m, n, rank, np.random.default_rng(seed))
         assert relerr(A, rmm.rand_low_rank(m, n, rank, np.random.default_rng(seed))) < 1e-13
         rs_r, rs_o = raw.RS1(rsko.SkOpGA(), npass, rulaw.orth, 1), orc.RS1(orc.SkOpGA(), npass, orc.orth, 1)
