@@ -11,6 +11,10 @@ agree (x, residual, per-iteration error history, sketch operators bit-for-bit, l
 factors) and writes the fixtures under ``tests/golden/``.  ``tests/test_oracle_golden.py``
 re-checks the oracle against those committed fixtures without needing the reference.
 
+Restated here: the sketching operators (Gaussian, SJLT, SRCT), SPO / SSO1 / SPU1, LSQR, the lifted preconditioned
+operator, PcSS2 (both branches), pcg / PcSS1, SPS1 (SVD and Nystrom preconditioners) / SPS2, RS1 / RF1 / QB1 / QB2 /
+QB3, SVD1, EVD1 / EVD2, the interpolative / CUR decompositions, and the reference's test-problem generators.
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py`` may import
 this module.  The product path (``parla_b200``) never does.
 """
