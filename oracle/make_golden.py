@@ -70,7 +70,7 @@ def digest(arr):
 
 
 def spo_case(name, m, n, seed, sketch, mode, delta, sf=4, tol=1e-12, iter_lim=100, cond=1.0,
-             store_S=True, rng_seed=1):
+             store_S=True, rng_seed=1, big=False):
     A, b = lsq_problem(m, n, seed, cond)
     ref_gen = Tape({'sjlt': rsko.SkOpSJ(8), 'gauss': rsko.SkOpGA(), 'srct': rsko.SkOpTC()}[sketch])
     orc_gen = Tape({'sjlt': orc.SkOpSJ(8), 'gauss': orc.SkOpGA(), 'srct': orc.SkOpTC()}[sketch])
@@ -97,6 +97,11 @@ def spo_case(name, m, n, seed, sketch, mode, delta, sf=4, tol=1e-12, iter_lim=10
     fx = dict(m=m, n=n, seed=seed, cond=cond, sketch=sketch, mode=mode, delta=delta, sf=sf, tol=tol,
               iter_lim=iter_lim, rng_seed=rng_seed, x=x_ref, errors=log_ref.errors,
               resid_norm=np.linalg.norm(r), A_sha=digest(A), b_sha=digest(b))
+    if big:
+        # b = A @ x0 + noise goes through a BLAS gemv whose summation order depends on the host; a problem this
+        # large is pinned by the hash of A (pure RNG output) and a probe of b instead of b's hash
+        del fx["b_sha"]
+        fx.update(b_probe=b[::4096].copy(), b_norm=np.linalg.norm(b))
     if sketch == 'sjlt':
         fx.update(S_sha=digest(rows) + digest(signs), vec_nnz=k)
         if store_S:
@@ -108,6 +113,35 @@ def spo_case(name, m, n, seed, sketch, mode, delta, sf=4, tol=1e-12, iter_lim=10
     else:
         fx.update(S_sha=digest(S_ref))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+
+
+def spo_rankdef_case(name, rng_seed, iter_lim=100, tol=1e-12):
+    """The reference's `consistent_lowrank` problem (test_overdet_least_squares.py:23-34; rank 5 of 10 columns)
+    through SPO(SkOpGA, 3, 'svd') (:408-411, with the tolerance the test meant: 1e-12).  Seed 1: the presolve is
+    exact and accepted; seed 4: R is non-square and the presolve is off, so LSQR starts from the origin
+    (least_squares.py:348-351)."""
+    import parla.utils.sketching as rusk
+    rng = np.random.default_rng(8923890298)
+    m, n, rank = 100, 10, 5
+    U = rusk.orthonormal_operator(m, rank, rng)
+    sv = rng.random(rank) + 1e-4
+    Vt = rusk.orthonormal_operator(rank, n, rng)
+    A = (U * sv) @ Vt
+    x0 = rng.standard_normal(n)
+    b = A @ x0
+    A2, b2, x02, Vt2 = orc.consistent_lowrank_problem()
+    assert relerr(A2, A) < 1e-14 and relerr(b2, b) < 1e-14
+    ref_gen, orc_gen = Tape(rsko.SkOpGA()), Tape(orc.SkOpGA())
+    x_ref, log_ref = rla.SPO(ref_gen, 3, 'svd')(A, b, 0.0, tol, iter_lim, np.random.default_rng(rng_seed), logging=True)
+    x_orc, log_orc = orc.SPO(orc_gen, 3, 'svd')(A, b, 0.0, tol, iter_lim, np.random.default_rng(rng_seed), logging=True)
+    assert np.array_equal(ref_gen.ops[0], orc_gen.ops[0])
+    e_x = relerr(x_orc, x_ref)
+    print(f"{name:28s} iters ref/orc {(log_ref.errors.size - 1, log_orc.errors.size - 1)}  |dx|/|x| {e_x:.2e}  "
+          f"|Ax-b| {np.linalg.norm(A @ x_ref - b):.1e}  min-norm gap {abs(np.linalg.norm(x_ref) - np.linalg.norm(Vt.T @ (Vt @ x0))):.1e}")
+    assert e_x < 1e-10 and log_ref.errors.size == log_orc.errors.size
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), rng_seed=rng_seed, iter_lim=iter_lim, tol=tol, x=x_ref,
+                        errors=log_ref.errors, resid_norm=np.linalg.norm(A @ x_ref - b), A=A, b=b, S=ref_gen.ops[0],
+                        x_minnorm=Vt.T @ (Vt @ x0))
 
 
 def srct_cases():
@@ -217,7 +251,8 @@ def sps_cases():
     sps_case("sps2_hiacc_500x50", 'sps2', 500, 50, 1e3, 'lin', 1.0, 1e-12, 50, rng_seed=42)
 
 
-def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pass=2, evd=False):
+def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pass=2, evd=False, big=False,
+                 spectrum_param=2.0):
     rng = np.random.default_rng(seed)
     if evd:
         B0 = rmm.rand_low_rank(m, rank, rank, rng)
@@ -225,8 +260,8 @@ def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pa
         A = 0.5 * (A + A.T)
         n = m
     else:
-        A = rmm.exponent_spectrum(m, n, rank, rng, 2.0)
-    A_orc = orc.exponent_spectrum(m, n, rank, np.random.default_rng(seed), 2.0) if not evd else A
+        A = rmm.exponent_spectrum(m, n, rank, rng, spectrum_param)
+    A_orc = orc.exponent_spectrum(m, n, rank, np.random.default_rng(seed), spectrum_param) if not evd else A
     assert relerr(A_orc, A) < 1e-13
 
     def build(lib, sko, orth):
@@ -256,12 +291,18 @@ def lowrank_case(name, m, n, rank, k, seed, blk=None, tol=np.nan, over=0, num_pa
     e_sp = float(np.max(np.abs(spec_orc - spec_ref)) / np.max(np.abs(spec_ref)))
     print(f"{name:28s} QB cols {Q_ref.shape[1]}  d(QB) {e_qb:.2e}  d(approx) {e_ap:.2e}  d(spec) {e_sp:.2e}")
     assert Q_ref.shape == Q_orc.shape and e_qb < 1e-10 and e_ap < 1e-10 and e_sp < 1e-12
+    extra = {}
+    if big:
+        # A is built with a LAPACK QR and GEMMs: bit-reproducible across hosts only for small shapes, so a large
+        # matrix is pinned by a probe and its norm (to 1e-13) instead of a hash
+        extra = dict(A_probe=A[::max(1, m // 16), ::max(1, n // 16)].copy(), A_fro=np.linalg.norm(A),
+                     spectrum_param=spectrum_param)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), m=m, n=n, rank=rank, k=k, seed=seed,
                         blk=-1 if blk is None else blk, tol=tol, over=over, num_pass=num_pass,
                         evd=evd, spec=spec_ref, qb_cols=Q_ref.shape[1],
                         approx_fro=np.linalg.norm(approx_ref),
-                        err_fro=np.linalg.norm(A - approx_ref), A_sha=digest(A),
-                        approx_probe=approx_ref[::max(1, m // 16), ::max(1, n // 16)])
+                        err_fro=np.linalg.norm(A - approx_ref), A_sha="" if big else digest(A),
+                        approx_probe=approx_ref[::max(1, m // 16), ::max(1, n // 16)], **extra)
 
 
 def qb3_evd2_cases():
@@ -369,6 +410,18 @@ if __name__ == "__main__":
     if "--only-sps" in sys.argv:
         sps_cases()
         sys.exit(0)
+    if "--only-big" in sys.argv:
+        # BASELINE.json configs[1] at 1/16 of its rows (2^18 x 2048, d = 8192): ~1 min of reference + oracle time
+        spo_case("spo_cfg2s_262144x2048", 262144, 2048, 0, 'sjlt', 'qr', 0.0, store_S=False, big=True)
+        # configs[3] scaled: 2^14 x 2^11, k = 128, two power iterations, QB1 and QB2(blk = 32)
+        lowrank_case("svd1_qb1_cfg4s_16384x2048", 16384, 2048, 1024, 128, 61, big=True, spectrum_param=50.0)
+        lowrank_case("svd1_qb2_cfg4s_16384x2048", 16384, 2048, 1024, 128, 61, blk=32, tol=0.0, big=True,
+                     spectrum_param=50.0)
+        sys.exit(0)
+    if "--only-rankdef" in sys.argv:
+        spo_rankdef_case("spo_gauss_svd_rankdef_seed1", 1)
+        spo_rankdef_case("spo_gauss_svd_rankdef_seed4", 4)
+        sys.exit(0)
     if "--only-spu" in sys.argv:
         spu_case("spu1_sjlt_800x50", 800, 50, 31)
         spu_case("spu1_sjlt_2000x96", 2000, 96, 32, cond=1e5)
@@ -397,4 +450,6 @@ if __name__ == "__main__":
     srct_cases()
     qb3_evd2_cases()
     id_cases()
-    print("golden fixtures written to", OUT)
+    spo_rankdef_case("spo_gauss_svd_rankdef_seed1", 1)
+    spo_rankdef_case("spo_gauss_svd_rankdef_seed4", 4)
+    print("golden fixtures written to", OUT, "(the large ones: rerun with --only-big)")

@@ -1186,3 +1186,96 @@ def saddle_problem(m, n, spectrum, delta, rng, rhs_scale=1.0):
     except sla.LinAlgError:
         x_opt = sla.lstsq(gram, rhs)[0]
     return A, b, c, x_opt, b - A @ x_opt
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Test problems of the reference's own least-squares suite (restated so the GPU box, which has no
+# /root/reference, can rebuild them): tests/test_drivers/test_optim/test_overdet_least_squares.py:11-112.
+# Each returns (A, b, x_opt, U, s, Vt) -- the fields of the reference's AlgTestHelper (:123-139).
+def simple_mat(n_rows, n_cols, scale, rng):
+    """tests/matmakers.py:24-31."""
+    rng = np.random.default_rng(rng)
+    A = rng.normal(0, 1, (n_rows, n_cols))
+    QA, RA = sla.qr(A)
+    damp = 1 / np.sqrt(1 + scale * np.arange(n_cols))
+    RA *= damp
+    return QA @ RA
+
+
+def lsq_test_problem(kind):
+    """kind in {'consistent_tall', 'consistent_lowrank', 'consistent_square', 'inconsistent_orthog',
+    'inconsistent_gen', 'inconsistent_stackid'}: test_overdet_least_squares.py:11-21, :23-34, :37-48, :51-68,
+    :71-93, :96-112 (same seeds, same order of RNG draws)."""
+    if kind == 'consistent_tall':
+        rng = np.random.default_rng(190489290)
+        m, n = 100, 10
+        A = simple_mat(m, n, scale=1, rng=rng)
+        U, s, Vt = sla.svd(A)
+        x = rng.standard_normal(n)
+        return A, A @ x, x, U, s, Vt
+    if kind in ('consistent_lowrank', 'consistent_square'):
+        low = kind == 'consistent_lowrank'
+        rng = np.random.default_rng(8923890298 if low else 3278992245)
+        m, n, rank = (100, 10, 5) if low else (10, 10, 10)
+        U = orthonormal_operator(m, rank, rng)
+        s = rng.random(rank) + 1e-4
+        Vt = orthonormal_operator(rank, n, rng)
+        A = (U * s) @ Vt
+        x = rng.standard_normal(n)
+        return A, A @ x, x, U, s, Vt
+    if kind == 'inconsistent_orthog':
+        n, m = 1000, 100
+        rng = np.random.default_rng(19837647834763)
+        U = orthonormal_operator(n, m, rng)
+        Vt = orthonormal_operator(m, m, rng)
+        s = rng.random(m) + 1e-4
+        A = (U * s) @ Vt
+        b = rng.standard_normal(n)
+        b = b - U @ (U.T @ b)
+        b *= 1e2 / sla.norm(b)
+        return A, b, np.zeros(m), U, s, Vt
+    if kind == 'inconsistent_gen':
+        rng = np.random.default_rng(897809809)
+        m, n, num_hi = 1000, 100, 30
+        num_lo = n - num_hi
+        hi_spec = 1e5 * np.ones(num_hi) + rng.random(num_hi)
+        lo_spec = np.ones(num_lo) + rng.random(num_lo)
+        spec = np.concatenate([hi_spec, lo_spec])
+        U = orthonormal_operator(m, n, rng)
+        Vt = orthonormal_operator(n, n, rng)
+        A = (U * spec) @ Vt
+        hi_x = rng.standard_normal(num_hi) / 1e5
+        lo_x = rng.standard_normal(num_lo)
+        x = np.concatenate([hi_x, lo_x])
+        b_orth = rng.standard_normal(m) * 1e2
+        b_orth -= U @ (U.T @ b_orth)
+        return A, A @ x + b_orth, x, U, spec, Vt
+    if kind == 'inconsistent_stackid':
+        rng = np.random.default_rng(2837592038243)
+        A = np.tile(np.eye(70), (10, 1))
+        m, n = A.shape
+        A = (A.T * rng.lognormal(size=(m,))).T
+        x0 = rng.standard_normal(size=(n,))
+        b = A @ x0 + rng.standard_normal(size=(m,))
+        U, spec, Vt = sla.svd(A, full_matrices=False)
+        x = Vt.T @ (U.T @ b) / spec
+        return A, b, x, U, spec, Vt
+    raise ValueError(kind)
+
+
+def consistent_lowrank_problem():
+    A, b, x, _, _, Vt = lsq_test_problem('consistent_lowrank')
+    return A, b, x, Vt
+
+
+def loglinear_fit(x, y):
+    """utils/stats.py:6-29: least-squares fit of log(y) ~ a + b x; returns ([a, b], R^2)."""
+    x = np.asarray(x, float).ravel()
+    y = np.asarray(y, float).ravel()
+    keep = y > 0
+    x, logy = x[keep], np.log(y[keep])
+    mat = np.column_stack([np.ones(x.size), x])
+    fit = sla.lstsq(mat, logy)[0]
+    ss_tot = np.sum((logy - np.mean(logy)) ** 2)
+    ss_res = np.sum((logy - mat @ fit) ** 2)
+    return fit, 1 - ss_res / ss_tot

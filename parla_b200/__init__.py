@@ -14,7 +14,7 @@ from .comps.rangefinders import RF1, RangeFinder
 from .comps.determiter.logging import SketchAndPrecondLog
 from .comps.determiter.saddle import PcSS1, PcSS2, PrecondSaddleSolver, pcss1, pcss2
 from .comps.determiter.pcg import pcg
-from .drivers.least_squares import SPO, SSO1, OverLstsqSolver, SPU1, UnderLstsqSolver
+from .drivers.least_squares import SPO, SAP1, SAP2, SSO1, OverLstsqSolver, SPU1, UnderLstsqSolver
 from .drivers.saddlesys import SPS1, SPS2, SaddleSolver, sps
 from .drivers.svd import SVD1, SVDecomposer
 from .drivers.evd import EVD1, EVD2, EVDecomposer

@@ -143,13 +143,14 @@ def _svd_via_gram(A_ske):
     return V, B / sigma, sigma
 
 
-def svd_right_precond(A_ske):
-    """parla/comps/preconditioning.py:70-79.  The small dense SVD is cuSOLVER glue; for
+def svd_right_precond(A_ske, exact=False):
+    """parla/comps/preconditioning.py:70-79.  ``exact=True`` forces the true SVD (callers that use U beyond
+    the presolve, or that need the rank decision).  The small dense SVD is cuSOLVER glue; for
     n >= 512 and a well-conditioned sketch it is replaced by the Gram/eigh route above (same M, U, sigma, Vh
     up to rotations inside clusters of equal singular values, which no caller can observe)."""
     A_ske = A_ske.contiguous()
     n = A_ske.shape[1]
-    if FAST_SVD and n >= FAST_SVD_MIN_N and A_ske.shape[0] >= n:
+    if FAST_SVD and not exact and n >= FAST_SVD_MIN_N and A_ske.shape[0] >= n:
         fast = _svd_via_gram(A_ske)
         if fast is not None:
             V, U, sigma = fast

@@ -145,8 +145,18 @@ class SSO1(OverLstsqSolver):
         _, W = _sketch(self.sketch_op_gen, d, A, b, delta, rng)
         log['time_sketch'] = quick_time() - tic
         tic = quick_time()
+        # la.lstsq(A_ske, b_ske, lapack_driver=...) (:184-186).  Householder QR + one triangular solve when the
+        # sketch has full numerical rank; otherwise the minimum-norm solution through the SVD of R with
+        # gelsd's cut-off (every scipy driver -- gelsd, gelsy, gelss -- is rank revealing, so all map here).
         K.geqrf(W, n_cols)
-        x_ske = K.trsv_upper(W[:n_cols, :n_cols], W[:n_cols, n_cols].contiguous())
+        R = W[:n_cols, :n_cols]
+        dabs = R.diagonal().abs()
+        dmin, dmax = (float(v) for v in torch.stack((dabs.min(), dabs.max())).cpu())
+        if dmin > torch.finfo(F64).eps * n_cols * dmax:
+            x_ske = K.trsv_upper(R, W[:n_cols, n_cols].contiguous())
+        else:
+            M, U_r, _, _ = rpc.svd_right_precond(torch.triu(R), exact=True)
+            x_ske = M @ (U_r.T @ W[:n_cols, n_cols])
         log['time_solve'] = quick_time() - tic
         return _to_host(x_ske, host), log
 
@@ -286,6 +296,22 @@ class SPO(OverLstsqSolver):
         return _to_host(x, host), log
 
     exec = __call__
+
+
+class SAP1(SPO):
+    """"SAP1" of the reference's change log (CHANGELOG.md:57): sketch-and-precondition with the QR
+    preconditioner, i.e. ``SPO(sketch_op_gen, sampling_factor, mode='qr')`` (least_squares.py:306-316)."""
+
+    def __init__(self, sketch_op_gen, sampling_factor):
+        super().__init__(sketch_op_gen, sampling_factor, mode='qr')
+
+
+class SAP2(SPO):
+    """"SAP2" (CHANGELOG.md:57): the SVD preconditioner, ``SPO(..., mode='svd')`` (least_squares.py:330-339);
+    handles rank-deficient sketches."""
+
+    def __init__(self, sketch_op_gen, sampling_factor):
+        super().__init__(sketch_op_gen, sampling_factor, mode='svd')
 
 
 class UnderLstsqSolver:

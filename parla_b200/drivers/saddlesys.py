@@ -245,7 +245,14 @@ class SPS2(SaddleSolver):
         b_top = b_loc.clone()
         b_ridge = torch.zeros(n, dtype=F64, device=dev) if delta > 0 else None
         if c is not None and _norm(c) > 0:
-            v = _mv(U, _mv(Vh, c) / sigma)
+            # v = pinv(A_ske_aug') c must satisfy A_ske_aug' v = c to working accuracy (it defines the transformed
+            # right-hand side).  With full column rank that is v = Q R^{-T} c -- one triangular solve against
+            # the Householder R, exact to eps * cond, whichever route produced (M, U, sigma, Vh); U from the
+            # Gram/eigh route is orthonormal only to eps * cond^2 and is used for the presolve alone.
+            if M.shape[1] == n:
+                v = _mv(Q, K.trsv_upper(R_qr, c, trans=True))
+            else:
+                v = _mv(U, _mv(Vh, c) / sigma)
             b_top -= S.rmatvec(v[:d].contiguous(), m_local=m_loc, row_offset=row_off)
             if delta > 0:
                 b_ridge -= v[d:]

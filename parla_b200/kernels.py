@@ -62,13 +62,17 @@ def _vec(t, name):
 
 
 class Workspace:
-    """Grow-only device scratch buffer (one per device), handed to the C ABI as (ptr, bytes)."""
+    """Grow-only device scratch buffers handed to the C ABI as (ptr, bytes): one per (device, stream, tag), so
+    work enqueued on different streams never shares partial-sum scratch.  A buffer that is outgrown goes back to
+    torch's caching allocator, which is stream-ordered for the stream that allocated it -- the same stream
+    that still has kernels using it -- so the hand-over is safe."""
 
     _bufs = {}
 
     @classmethod
     def get(cls, device, nbytes, tag="main"):
-        key = (torch.device(device).index, tag)
+        device = torch.device(device)
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

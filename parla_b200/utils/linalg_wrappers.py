@@ -33,11 +33,21 @@ def lup(M):
     return U.T.contiguous(), L.T.contiguous(), P.T.contiguous()
 
 
+def _pinv_apply(operator, target):
+    """pinv(operator) @ target through a thin SVD with LAPACK gelsd's cut-off (singular values below
+    eps * sigma_max are treated as zero): the minimum-norm least-squares solution also when ``operator`` is
+    rank deficient, which torch.linalg.lstsq's only CUDA driver ('gels', full rank assumed) does not give."""
+    U, s, Vh = torch.linalg.svd(operator, full_matrices=False)
+    cut = torch.finfo(operator.dtype).eps * (s[0] if s.numel() else 0.0)
+    sinv = torch.where(s > cut, 1.0 / s, torch.zeros_like(s))
+    return Vh.T @ (sinv.unsqueeze(1) * (U.T @ target))
+
+
 def apply_pinv_on_left(target, operator):
-    """linalg_wrappers.py:27-30: pinv(operator) @ target  (tall full-rank ``operator``: QR-based least squares)."""
-    return torch.linalg.lstsq(operator, target).solution
+    """linalg_wrappers.py:27-30: pinv(operator) @ target  (scipy ``lstsq`` / gelsd semantics)."""
+    return _pinv_apply(operator, target).contiguous()
 
 
 def apply_pinv_on_right(target, operator):
     """linalg_wrappers.py:33-36: target @ pinv(operator)."""
-    return torch.linalg.lstsq(operator.T.contiguous(), target.T.contiguous()).solution.T.contiguous()
+    return _pinv_apply(operator.T.contiguous(), target.T.contiguous()).T.contiguous()

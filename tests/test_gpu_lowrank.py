@@ -8,8 +8,8 @@ import pytest
 import torch
 
 from oracle import parla_oracle as orc
-from tests.helpers import (EVD2_FIXTURES, ID_FIXTURES, LOWRANK_FIXTURES, QB3_FIXTURES, check_id_fixture, digest,
-                           id_matrix_from_fixture, load_golden, lowrank_matrix_from_fixture)
+from tests.helpers import (EVD2_FIXTURES, ID_FIXTURES, LOWRANK_BIG_FIXTURES, LOWRANK_FIXTURES, QB3_FIXTURES,
+                           check_id_fixture, digest, id_matrix_from_fixture, load_golden, lowrank_matrix_from_fixture)
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings("ignore")
@@ -65,6 +65,36 @@ def test_lowrank_matches_reference_fixture(rla, name):
     sr, sc = max(1, A.shape[0] // 16), max(1, A.shape[1] // 16)
     assert np.max(np.abs(approx[::sr, ::sc] - fx["approx_probe"])) <= 1e-10 * float(fx["approx_fro"])
     assert abs(np.linalg.norm(A - approx) - float(fx["err_fro"])) <= 1e-10 * float(fx["approx_fro"])
+
+
+@pytest.mark.parametrize("name", LOWRANK_BIG_FIXTURES)
+def test_lowrank_cfg4_scaled_parity(rla, name):
+    """BASELINE.json configs[3] scaled as SURVEY.md 8(d) prescribes: 2^14 x 2^11, decaying spectrum, k = 128, two
+    power iterations (RS1), QB1 and QB2(blk = 32); SVD1 against (1) the REFERENCE's spectrum / approximation
+    (fixture) and (2) the oracle run live on the same matrix with the same numpy Gaussian test matrices.
+    Tolerances: s to 1e-10 s_0, |U s V' - (U s V')_ref|_F <= 1e-10 |A|_F."""
+    fx = load_golden(name)
+    m, n, k = int(fx["m"]), int(fx["n"]), int(fx["k"])
+    A = orc.exponent_spectrum(m, n, int(fx["rank"]), np.random.default_rng(int(fx["seed"])), float(fx["spectrum_param"]))
+    fro = float(fx["A_fro"])
+    assert abs(np.linalg.norm(A) - fro) <= 1e-13 * fro
+    assert np.max(np.abs(A[::m // 16, ::n // 16] - fx["A_probe"])) <= 1e-13 * np.max(np.abs(fx["A_probe"]))
+    blk, tol = int(fx["blk"]), float(fx["tol"])
+
+    def build(lib, orth):
+        rf = lib.RF1(lib.RS1(orc.SkOpGA(), int(fx["num_pass"]), orth, 1))
+        return lib.SVD1(lib.QB1(rf) if blk < 0 else lib.QB2(rf, blk, False))
+
+    U, s, Vh = build(rla, rla.orth)(dev(A), k, tol, 0, np.random.default_rng(7))
+    U, s, Vh = U.cpu().numpy(), s.cpu().numpy(), Vh.cpu().numpy()
+    assert s.shape == fx["spec"].shape and np.max(np.abs(s - fx["spec"])) <= 1e-10 * fx["spec"][0]
+    approx = (U * s) @ Vh
+    assert np.max(np.abs(approx[::m // 16, ::n // 16] - fx["approx_probe"])) <= 1e-10 * float(fx["approx_fro"])
+    assert abs(np.linalg.norm(A - approx) - float(fx["err_fro"])) <= 1e-10 * fro
+    assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-9 and np.linalg.norm(Vh @ Vh.T - np.eye(k)) < 1e-9
+    Uo, so, Vho = build(orc, orc.orth)(A, k, tol, 0, np.random.default_rng(7))            # live oracle, full matrices
+    assert np.max(np.abs(s - so)) <= 1e-10 * so[0]
+    assert np.linalg.norm(approx - (Uo * so) @ Vho) <= 1e-10 * fro
 
 
 @pytest.mark.parametrize("shape,rank", [((200, 50), 15), ((50, 200), 15), ((200, 50), 50)])

@@ -177,3 +177,23 @@ def test_sps2_native_operators_and_c_zero(rla):
     assert np.linalg.norm(x1 - np.linalg.solve(G, A.T @ b - c)) <= 1e-7 * np.linalg.norm(x1)
     with pytest.raises(ValueError):
         rla.sps(A, b, c, delta, 1e-10, 100, 3, method='nope')
+
+
+def test_sps2_wide_ridge_nonzero_c_against_oracle(rla):
+    """SPS2 with n >= 512 (where svd_right_precond takes the Gram/eigh route), c != 0, delta > 0, tol 1e-12:
+    the transformed right-hand side needs A_ske' v = c to working accuracy (saddlesys.py:287-295); v comes from
+    a triangular solve against the Householder R, not from the Gram route's U (orthonormal only to eps cond^2)."""
+    rng = np.random.default_rng(77)
+    m, n, delta = 6000, 576, 0.4
+    A = rng.standard_normal((m, n)) * np.logspace(0, 2, n)
+    b = rng.standard_normal(m)
+    c = rng.standard_normal(n)
+    S = orc.sjlt_operator(3 * n, m, np.random.default_rng(9), 8)
+    x_ref, y_ref, log_ref = orc.SPS2(Replay(S), 3)(A, b, c, delta, 1e-12, 100, None, logging=True)
+    x, y, log = rla.SPS2(Replay(S), 3)(dev(A), dev(b), dev(c), delta, 1e-12, 100, None, logging=True)
+    x, y = x.cpu().numpy(), y.cpu().numpy()
+    assert np.linalg.norm(x - x_ref) <= 1e-9 * np.linalg.norm(x_ref)
+    assert np.linalg.norm(y - y_ref) <= 1e-9 * np.linalg.norm(y_ref)
+    assert abs(log.errors.size - log_ref.errors.size) <= 1
+    x_opt = np.linalg.solve(A.T @ A + delta * np.eye(n), A.T @ b - c)
+    assert np.linalg.norm(x - x_opt) <= 1e-9 * np.linalg.norm(x_opt)

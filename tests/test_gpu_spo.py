@@ -11,8 +11,8 @@ import pytest
 import torch
 
 from oracle import parla_oracle as orc
-from tests.helpers import (SPO_FIXTURES, SPU_FIXTURES, Replay, load_golden, problem_from_fixture, sjlt_from_fixture,
-                           spu_problem_from_fixture)
+from tests.helpers import (SPO_FIXTURES, SPO_RANKDEF_FIXTURES, SPU_FIXTURES, Replay, load_golden,
+                           problem_from_fixture, sjlt_from_fixture, spu_problem_from_fixture)
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings("ignore")
@@ -65,6 +65,73 @@ def test_spo_cfg1_full_size_parity(rla):
     assert abs(np.linalg.norm(A @ x - b) - float(fx["resid_norm"])) <= TOL_X * float(fx["resid_norm"])
     assert abs(log.errors.size - fx["errors"].size) <= 1
     assert log.passes_over_A <= log.iters + 4            # sketch + presolve/init + iterations + final
+
+
+def test_spo_cfg2_scaled_parity(rla):
+    """BASELINE.json configs[1] at 1/16 of its rows -- 2^18 x 2048, SJLT k = 8, d = 4n = 8192, tol 1e-12 -- against
+    the REFERENCE's output (oracle/make_golden.py --only-big; the reference's own SJLT is regenerated from its
+    seed and hash-checked, A is hash-checked).  This is the size at which the windowed SJLT apply, the 128-column
+    block-reflector QR and the split-K DMMA GEMMs all engage."""
+    fx = load_golden("spo_cfg2s_262144x2048")
+    A, b = problem_from_fixture(fx)
+    m, n = A.shape
+    S = sjlt_from_fixture(fx, 4 * n, m)
+    x, log = rla.SAP1(Replay(S), 4)(dev(A), dev(b), 0.0, 1e-12, 100, None)
+    x = x.cpu().numpy()
+    assert np.linalg.norm(x - fx["x"]) <= TOL_X * np.linalg.norm(fx["x"])
+    r = np.linalg.norm(A @ x - b)
+    assert abs(r - float(fx["resid_norm"])) <= TOL_X * float(fx["resid_norm"])
+    assert abs(log.errors.size - fx["errors"].size) <= 1                       # iteration count +-1
+    k = min(log.errors.size, fx["errors"].size)
+    assert np.allclose(log.errors[:k], fx["errors"][:k], rtol=1e-6, atol=1e-11 * fx["errors"][0])
+
+
+@pytest.mark.parametrize("name", SPO_RANKDEF_FIXTURES)
+def test_spo_svd_rank_deficient_matches_reference(rla, name):
+    """The reference's `consistent_lowrank` problem (test_overdet_least_squares.py:23-34, :408-411 with the
+    intended tol 1e-12): rank 5 of 10 columns, SPO(mode='svd') truncates the preconditioner to the numerical rank
+    (preconditioning.py:74-77); with seed 4 the presolve is rejected because R is non-square
+    (least_squares.py:348-351) and LSQR starts from the origin."""
+    fx = load_golden(name)
+    A, b, S = fx["A"], fx["b"], fx["S"]
+    for alg in (rla.SPO(Replay(S), 3, 'svd'), rla.SAP2(Replay(S), 3)):
+        x, log = alg(dev(A), dev(b), 0.0, float(fx["tol"]), int(fx["iter_lim"]), None)
+        x = x.cpu().numpy()
+        assert np.linalg.norm(x - fx["x"]) <= TOL_X * np.linalg.norm(fx["x"])
+        assert np.linalg.norm(x - fx["x_minnorm"]) <= 1e-9 * np.linalg.norm(fx["x_minnorm"])   # minimum-norm solution
+        assert np.linalg.norm(A @ x - b) <= 1e-12 * np.linalg.norm(b)
+        assert log.errors.size == fx["errors"].size
+        big = fx["errors"] > 1e-9 * fx["errors"][0]
+        assert np.allclose(log.errors[big], fx["errors"][big], rtol=1e-6)
+
+
+def test_sap1_sap2_are_spo_modes(rla):
+    """CHANGELOG.md:57 names: SAP1 == SPO(mode='qr'), SAP2 == SPO(mode='svd'); bit-identical results."""
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((3000, 70)); b = rng.standard_normal(3000)
+    Ad, bd = dev(A), dev(b)
+    for cls, mode in ((rla.SAP1, 'qr'), (rla.SAP2, 'svd')):
+        alg = cls(rla.SkOpSJ(8), 4)
+        assert isinstance(alg, rla.SPO) and alg.mode == mode
+        x1, l1 = alg(Ad, bd, 0.0, 1e-12, 100, 5)
+        x2, l2 = rla.SPO(rla.SkOpSJ(8), 4, mode)(Ad, bd, 0.0, 1e-12, 100, 5)
+        assert torch.equal(x1, x2) and np.array_equal(l1.errors, l2.errors)
+        assert alg.exec.__func__ is rla.SPO.__call__
+
+
+def test_sso1_rank_deficient_sketch_is_min_norm(rla):
+    """SSO1 calls la.lstsq (gelsd: rank revealing, minimum norm; least_squares.py:184-186).  A sketch with
+    dependent columns must give the pseudo-inverse solution, not inf/nan from a triangular solve."""
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((1500, 24))
+    A[:, 20:] = A[:, :4] @ rng.standard_normal((4, 4))                  # rank 20
+    b = rng.standard_normal(1500)
+    S = orc.sjlt_operator(96, 1500, np.random.default_rng(2), 8)
+    x_ref, _ = orc.SSO1(Replay(S), 4)(A, b, 0.0, np.nan, 1, None)
+    x, _ = rla.SSO1(Replay(S), 4)(dev(A), dev(b), 0.0, np.nan, 1, None)
+    x = x.cpu().numpy()
+    assert np.all(np.isfinite(x))
+    assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
 
 
 @pytest.mark.parametrize("mode", ["qr", "svd", "chol"])

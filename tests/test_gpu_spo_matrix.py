@@ -1,0 +1,128 @@
+"""GPU: the reference's own TestSPO matrix (parla/tests/test_drivers/test_optim/test_overdet_least_squares.py:
+265-411) run against the device drivers: {SRCT, Gaussian, SJLT} x {qr, chol, svd} convergence-rate tests (with and
+without ridge, on `inconsistent_gen` and `inconsistent_stackid`), and the consistent / inconsistent problem
+families over the reference's seeds [1, 4, 15, 31, 42].  The problems are the reference's (restated in
+oracle/parla_oracle.py::lsq_test_problem, same seeds and draw order); the assertions are AlgTestHelper's
+(:141-204) with the reference's tolerances.  The sketching operators are the Philox-native ones: these are
+property tests, the bit-level comparisons with replayed operators live in test_gpu_spo.py."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parla_oracle as orc
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+SEEDS = [1, 4, 15, 31, 42]                                    # TestOverLstsqSolver.SEEDS (:209)
+_PROBLEMS = {}
+
+
+@pytest.fixture(scope="module")
+def rla():
+    import parla_b200
+    return parla_b200
+
+
+def problem(kind):
+    if kind not in _PROBLEMS:
+        _PROBLEMS[kind] = orc.lsq_test_problem(kind)
+    return _PROBLEMS[kind]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+class Helper:
+    """AlgTestHelper (:115-204) on numpy copies of the device result."""
+
+    def __init__(self, kind):
+        self.A, self.b, self.x_opt, self.U, self.s, self.Vt = problem(kind)
+        self.x_approx = None
+
+    def x_angle(self, tol):
+        y_opt = self.Vt @ self.x_opt
+        y = self.Vt @ self.x_approx
+        if np.linalg.norm(y_opt) < 1e-8:
+            assert abs(np.linalg.norm(y) - np.linalg.norm(y_opt)) <= tol
+        else:
+            assert np.dot(y / np.linalg.norm(y), y_opt / np.linalg.norm(y_opt)) >= 1 - tol
+
+    def x_norm(self, tol):
+        norm, norm_opt = np.linalg.norm(self.Vt @ self.x_approx), np.linalg.norm(self.Vt @ self.x_opt)
+        assert norm <= (1 + tol) * norm_opt + tol and (1 - tol) * norm_opt <= norm
+
+    def delta_x(self, tol):
+        d = np.linalg.norm(self.x_opt - self.x_approx)
+        assert d / (1 + min(np.linalg.norm(self.x_opt), np.linalg.norm(self.x_approx))) <= tol
+
+    def residual_proj(self, tol):
+        r = self.A @ self.x_approx - self.b
+        assert np.linalg.norm(self.U @ (self.U.T @ r)) / np.linalg.norm(r) <= tol
+
+    def objective(self, tol):
+        assert np.linalg.norm(self.b - self.A @ self.x_approx) <= np.linalg.norm(self.b - self.A @ self.x_opt) + tol
+
+
+def sketcher(rla, name):
+    return {"srct": rla.SkOpTC(), "gauss": rla.SkOpGA(), "sjlt": rla.SkOpSJ(vec_nnz=8)}[name]
+
+
+@pytest.mark.parametrize("mode", ["qr", "chol", "svd"])
+@pytest.mark.parametrize("sk", ["srct", "gauss", "sjlt"])
+def test_convergence_rate(rla, sk, mode):
+    """test_{srct,gaussian,sjlt}_{qr,chol,svd} (:275-300, :322-347, :370-395) via _test_convergence_rate (:237-256)."""
+    sap = rla.SPO(sketcher(rla, sk), sampling_factor=2, mode=mode)
+    for kind, ridge in (("inconsistent_gen", False), ("inconsistent_gen", True), ("inconsistent_stackid", False)):
+        ath = Helper(kind)
+        delta = 0.25 if ridge else 0.0
+        x, log = sap(dev(ath.A), dev(ath.b), delta, 1e-12, 100, np.random.default_rng(34998751340), logging=True)
+        fit, r2 = orc.loglinear_fit(np.arange(log.errors.size - 1), log.errors[1:])
+        assert r2 >= 0.95, (kind, ridge, r2)                  # linear convergence
+        assert fit[1] < -0.3, (kind, ridge, fit)              # faster than exp(-0.3 t)
+        assert log.errors[-1] <= 1e-6
+        if ridge:
+            n = ath.A.shape[1]
+            ath.x_opt = np.linalg.lstsq(np.vstack((ath.A, delta ** 0.5 * np.eye(n))),
+                                        np.hstack((ath.b, np.zeros(n))), rcond=None)[0]
+            ath.x_approx = x.cpu().numpy()
+            ath.delta_x(1e-6)
+
+
+@pytest.mark.parametrize("mode", ["qr", "chol", "svd"])
+@pytest.mark.parametrize("kind,sf,alg_tol,iter_lim,test_tol", [
+    ("consistent_tall", 1, 0.0, 1, 1e-12),                    # :302-305, :349-352, :397-400
+    ("consistent_square", 1, 0.0, 1, 1e-10),                  # :307-310 (1e-12 for qr), :354-358, :402-406
+    ("inconsistent_orthog", 3, 1e-12, 100, 1e-6),             # :312-315, :360-363, :408 ff
+    ("inconsistent_gen", 3, 1e-12, 100, 1e-6),                # :317-320, :365-368
+])
+def test_problem_families(rla, mode, kind, sf, alg_tol, iter_lim, test_tol):
+    ath = Helper(kind)
+    sap = rla.SPO(rla.SkOpGA(), sampling_factor=sf, mode=mode)
+    Ad, bd = dev(ath.A), dev(ath.b)
+    for seed in SEEDS:
+        x, _ = sap(Ad, bd, 0.0, alg_tol, iter_lim, np.random.default_rng(seed))
+        ath.x_approx = x.cpu().numpy()
+        if kind.startswith("consistent"):                     # run_consistent (:224-235)
+            ath.x_norm(test_tol)
+            ath.x_angle(test_tol)
+            ath.objective(test_tol)
+        else:                                                 # run_inconsistent (:211-222)
+            ath.residual_proj(test_tol)
+            ath.x_angle(test_tol)
+            ath.x_norm(test_tol)
+
+
+def test_consistent_lowrank_svd(rla):
+    """:408-411 (tol as intended, 1e-12; iter_lim 100 so the rejected-presolve seeds can converge)."""
+    ath = Helper("consistent_lowrank")
+    sap = rla.SAP2(rla.SkOpGA(), 3)
+    Ad, bd = dev(ath.A), dev(ath.b)
+    for seed in SEEDS:
+        x, _ = sap(Ad, bd, 0.0, 1e-12, 100, np.random.default_rng(seed))
+        ath.x_approx = x.cpu().numpy()
+        ath.x_norm(1e-6)
+        ath.x_angle(1e-6)
+        ath.objective(1e-6)
