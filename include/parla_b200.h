@@ -28,6 +28,9 @@ const char* pla_last_error(void);
 int pla_num_sms(void);
 /* Number of kernels this library has launched in this process so far (bench.py's gpu_launches). */
 long long pla_launch_count(void);
+/* Account for kernels launched on the library's behalf by a CUDA-graph replay (the graph was captured from
+ * this library's own launches; a replay does not pass through the entry points that count).           */
+void pla_note_launches(long long n);
 /* Measurement hook: `iters` x 8 independent DMMA.8x8x4 per warp, 8 warps per CTA, ctas_per_sm CTAs per SM.
  * Used once to find the FP64 tensor-pipe peak the Gaussian sketch is graded against.               */
 int pla_dmma_probe(int iters, int ctas_per_sm, double* sink, void* stream);

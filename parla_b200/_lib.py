@@ -18,6 +18,7 @@ SIGNATURES = {
     "pla_last_error": (C.c_char_p, []),
     "pla_num_sms": (c_int, []),
     "pla_launch_count": (C.c_longlong, []),
+    "pla_note_launches": (None, [C.c_longlong]),
     "pla_dmma_probe": (c_int, [c_int, c_int, c_vp, c_vp]),
     "pla_stream_pass_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "pla_stream_pass_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_int,

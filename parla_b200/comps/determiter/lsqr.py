@@ -7,6 +7,8 @@ A, (an all-reduce when row-sharded,) one transposed solve and one recurrence ker
 convergence flag lives in device memory; kernels turn into no-ops once it is set, so the host
 polls it a couple of iterations late through pinned memory instead of synchronising every step.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -16,6 +18,30 @@ from ...parallel import allreduce_
 F64 = torch.float64
 POLL_LAG = 2      # iterations the host may run ahead of the device-side stopping test
 _POLL_CACHE = {}
+# An iteration over a small A is launch-bound (~9 launches of a few microseconds each): below this many local
+# elements of A it is captured once into a CUDA graph and replayed (the device-side stop flag already turns
+# every kernel of a replay after convergence into a no-op).  Single-GPU only: no collective inside the graph.
+GRAPH_MAX_ELEMS = int(os.environ.get("PLA_LSQR_GRAPH_MAX_ELEMS", 1 << 27))
+USE_GRAPH = os.environ.get("PLA_LSQR_GRAPH", "1") != "0"
+_CAPTURE_STREAMS = {}
+
+
+def _capture_iteration(dev, n_max, body):
+    """Capture ``body()`` (kernel launches on the current stream, no allocation) into a CUDA graph."""
+    key = torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream()
+    side, cur = _CAPTURE_STREAMS[key], torch.cuda.current_stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        K.reserve_pass_workspace(dev, n_max)          # per-stream scratch exists before the capture starts
+        side.wait_stream(cur)
+        l0 = K.launch_count()
+        graph.capture_begin(capture_error_mode="thread_local")
+        body()
+        graph.capture_end()
+        nodes = K.launch_count() - l0
+    return graph, nodes
 
 
 def _poll_buffers():
@@ -66,7 +92,10 @@ def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=F
             A.atb = zss[:A.n].clone()
         else:
             A.bidiag_pass(x0, u, ub, zss, xw, t, sa=-1.0, su=1.0)
-    K.lsqr_init(t, zss, bsq, atol, btol, conlim, iter_lim, x0, x, v, w, dstate, istate)
+    # the recurrence kernels read |u~|^2 at index len(x) of their `zss` argument; zss holds it at index A.n, which
+    # is len(x) only for a full-rank preconditioner (rank-truncated SVD mode: len(x) = rank < A.n)
+    zs = zss[A.n - n:]
+    K.lsqr_init(t, zs, bsq, atol, btol, conlim, iter_lim, x0, x, v, w, dstate, istate)
 
     sc = dstate[K.LSQR_SA:K.LSQR_SA + 2]
     istop_dev = istate[0:1]
@@ -76,18 +105,31 @@ def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=F
         pinned[slot].copy_(istate, non_blocking=True)
         events[slot].record()
 
+    def iteration():
+        A.bidiag_pass(v, u, ub, zss, xw, t, sc=sc, istop=istop_dev)
+        K.lsqr_step(t, zs, x, v, w, dstate, istate, hist)
+
     post(0)
     events[0].synchronize()
     launched = 0
     if int(pinned[0][0]) == 0:
+        graph = None
+        if USE_GRAPH and A.group is None and A.m_local * A.n <= GRAPH_MAX_ELEMS and iter_lim > 2:
+            passes0 = A.passes
+            graph, nodes = _capture_iteration(dev, max(A.n, n), iteration)
+            A.passes = passes0                  # capturing enqueues nothing
         for it in range(iter_lim):
             if it >= POLL_LAG:
                 slot = (it - POLL_LAG) % (POLL_LAG + 1)
                 events[slot].synchronize()
                 if int(pinned[slot][0]) != 0:
                     break
-            A.bidiag_pass(v, u, ub, zss, xw, t, sc=sc, istop=istop_dev)
-            K.lsqr_step(t, zss, x, v, w, dstate, istate, hist)
+            if graph is None:
+                iteration()
+            else:
+                graph.replay()
+                A.passes += 1
+                K.note_launches(nodes)
             launched += 1
             post(it % (POLL_LAG + 1))
     torch.cuda.current_stream().synchronize()

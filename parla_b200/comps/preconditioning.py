@@ -37,6 +37,7 @@ class PrecondOperator:
         self.shape = (self.m + (self.n if self.delta > 0 else 0), self.rank)
         self.passes = 0
         self.atb = None          # cache of A^T b when a pass happened to produce it
+        self._zt = None          # scratch of precond_t (rank + 1 doubles), allocated once
 
     # ---- M and M^T on n-vectors (preconditioning.py:40-41 / :56-57)
     def precond(self, z, out=None, istop=None):
@@ -50,10 +51,12 @@ class PrecondOperator:
     def precond_t(self, w, out=None, istop=None):
         if self.tri:
             return K.trsv_upper(self.R, w, trans=True, out=out, istop=istop)
-        zss = K.stream_pass(self.R, u=w, flags=K.PASS_AXPY, istop=istop)
         if out is None:
-            return zss[:self.rank]
-        out.copy_(zss[:self.rank])     # (after LSQR has stopped nothing downstream reads `out`)
+            return K.stream_pass(self.R, u=w, flags=K.PASS_AXPY, istop=istop)[:self.rank]
+        if self._zt is None:
+            self._zt = torch.empty(self.rank + 1, dtype=F64, device=w.device)
+        K.stream_pass(self.R, u=w, zss=self._zt, flags=K.PASS_AXPY, istop=istop)
+        out.copy_(self._zt[:self.rank])     # (after LSQR has stopped nothing downstream reads `out`)
         return out
 
     # ---- one Golub-Kahan half-step pair in a single read of A

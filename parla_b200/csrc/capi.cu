@@ -84,6 +84,7 @@ extern "C" int pla_version(void) { return 100; }
 extern "C" const char* pla_last_error(void) { return g_err; }
 extern "C" int pla_num_sms(void) { return num_sms(); }
 extern "C" long long pla_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void pla_note_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" size_t pla_sumsq_workspace_bytes(int64_t n) {
     (void)n;

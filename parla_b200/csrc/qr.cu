@@ -535,29 +535,533 @@ __global__ void __launch_bounds__(256) qr_form_v_kernel(const double* __restrict
     }
 }
 
-// T (JB x JB upper, ld = QR_NBO) from the Gram matrix G = Vx^T Vx and tau (LAPACK dlarft, forward columnwise).
-__global__ void __launch_bounds__(QR_NBO) qr_build_tbig_kernel(const double* __restrict__ G, const double* __restrict__ tau,
-                                                               int JB, double* T) {
-    extern __shared__ double tb_smem[];
-    double* Ts = tb_smem;                       // [QR_NBO][QR_NBO + 1]
-    double* gcol = Ts + QR_NBO * (QR_NBO + 1);  // [QR_NBO]
-    const int r = threadIdx.x;
-    for (int c = 0; c < QR_NBO; ++c) Ts[r * (QR_NBO + 1) + c] = 0.0;
+// ================================================================================================
+// Cooperative block factorisation: ONE launch factors a whole 128-column block.
+//
+// The block's rows are spread over G co-resident CTAs (cooperative launch, one per SM) and stay in shared
+// memory for the whole factorisation.  Cross-CTA sums travel as NCCL-"LL"-style 16-byte lines
+// {lo, flag, hi, flag} in global memory (8-byte-atomic halves carrying their own epoch flag), so an
+// all-to-all exchange costs one L2 write + one L2 read and needs no barrier, fence or atomic:
+//   * per column: every CTA publishes <= 16 partial sums (|x|^2 of the column and its dots with the rest of
+//     the 16-column sub-panel), polls the G x 16 lines of the others and reduces them in a fixed order --
+//     every CTA computes bit-identical beta / tau / scale;
+//   * per 16-column sub-panel: W = V^T C for the rest of the block and the sub-panel's Gram matrix V^T V are
+//     reduce-scattered (plain partials + flag barrier, each CTA sums one slice over all CTAs in a fixed
+//     order) and all-gathered as LL lines; W2 = T^T W comes from the forward substitution
+//     w2_k = tau_k (w_k - sum_{l<k} G_lk w2_l)   (T^{-1} = striu(V^T V) + diag(1/tau); no division, tau = 0 ok),
+//     so T is never formed; C -= V W2 is local.
+// The kernel also emits the explicit reflector block Vx for the tensor-core update of the columns to the
+// right of the block.  Same arithmetic (LAPACK dlarfg/dlarfb conventions) as the panel kernels above.
+constexpr int QB_THREADS = 256;
+constexpr int QB_LDP = QR_NBO + 1;           // 129 doubles: conflict-free column walks
+constexpr int QB_MAXG = 160;                 // >= number of SMs
+constexpr int QB_RPC_MAX = 160;              // rows per CTA (shared-memory limit)
+constexpr int QB_WLD = QR_NBO - QR_NB;       // 112: leading dimension of the W totals
+constexpr int QB_NV = QR_NB * QB_WLD + QR_NB * QR_NB;   // 2048 values per reduce-scatter
+
+struct __align__(16) LLLine { uint32_t lo, f1, hi, f2; };
+
+__device__ __forceinline__ void ll_store(LLLine* p, double v, uint32_t flag, bool pred = true) {
+    const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    // predicated in PTX (never a branch): the column step must stay free of intra-warp divergence
+    asm volatile("{\n\t.reg .pred pq;\n\tsetp.ne.u32 pq, %5, 0;\n\t"
+                 "@pq st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "r"(lo), "r"(flag), "r"(hi), "r"(flag), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const LLLine* p, uint32_t flag, double& v) {
+    uint32_t lo, f1, hi, f2;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p)
+                 : "memory");
+    v = __hiloint2double((int)hi, (int)lo);
+    return f1 == flag && f2 == flag;
+}
+__device__ __forceinline__ double ll_load(const LLLine* p, uint32_t flag) {
+    double v;
+    while (!ll_try_load(p, flag, v)) {}
+    return v;
+}
+// Four LL lines at p + i * stride_bytes (i = 0..3), line i loaded iff bit i of `mask`: ONE asm block, so the four
+// 16-byte loads issue back to back and their L2 round trips overlap (separate asm statements interleaved with the
+// flag tests were serialised: ~750 cycles per line and poll).  w0 = {lo, flag}, w1 = {hi, flag} of each line.
+template <int STRIDE>
+__device__ __forceinline__ void ll_load4(const void* p, unsigned mask, unsigned long long (&w0)[4],
+                                         unsigned long long (&w1)[4]) {
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %9, 1;\n\tsetp.ne.u32 p0, t, 0;\n\t"
+        "and.b32 t, %9, 2;\n\tsetp.ne.u32 p1, t, 0;\n\t"
+        "and.b32 t, %9, 4;\n\tsetp.ne.u32 p2, t, 0;\n\t"
+        "and.b32 t, %9, 8;\n\tsetp.ne.u32 p3, t, 0;\n\t"
+        "@p0 ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%8];\n\t"
+        "@p1 ld.relaxed.gpu.global.v2.u64 {%2, %3}, [%8 + %10];\n\t"
+        "@p2 ld.relaxed.gpu.global.v2.u64 {%4, %5}, [%8 + %11];\n\t"
+        "@p3 ld.relaxed.gpu.global.v2.u64 {%6, %7}, [%8 + %12];\n\t}"
+        : "+l"(w0[0]), "+l"(w1[0]), "+l"(w0[1]), "+l"(w1[1]), "+l"(w0[2]), "+l"(w1[2]), "+l"(w0[3]), "+l"(w1[3])
+        : "l"(p), "r"(mask), "n"(STRIDE), "n"(2 * STRIDE), "n"(3 * STRIDE)
+        : "memory");
+}
+// line received (both halves carry `flag`)?  -> value
+__device__ __forceinline__ bool ll_ready(unsigned long long w0, unsigned long long w1, uint32_t flag, double& v) {
+    v = __hiloint2double((int)(uint32_t)w1, (int)(uint32_t)w0);
+    return (uint32_t)(w0 >> 32) == flag && (uint32_t)(w1 >> 32) == flag;
+}
+__device__ __forceinline__ void st_shared_pred(double* p, double v, bool pred) {
+    asm volatile("{\n\t.reg .pred pq;\n\tsetp.ne.u32 pq, %2, 0;\n\t@pq st.shared.f64 [%0], %1;\n\t}"
+                 ::"r"(smem_u32(p)), "d"(v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ void st_global_pred(double* p, double v, bool pred) {
+    asm volatile("{\n\t.reg .pred pq;\n\tsetp.ne.u32 pq, %2, 0;\n\t@pq st.global.f64 [%0], %1;\n\t}"
+                 ::"l"(p), "d"(v), "r"((uint32_t)pred) : "memory");
+}
+
+struct BlockParams {
+    double* A; long long lda; long long M;
+    long long J0; int JB;          // block = columns [J0, J0 + JB), rows [J0, M)
+    double* tau;                   // tau + J0
+    double* Vx;                    // out: (M - J0) x 128 explicit reflectors (unit diagonal, zeros above / right of JB)
+    int rpc;                       // rows per CTA (multiple of 16)
+    LLLine* ll_step;               // [2][16][QB_MAXG] partials, ONE line per 32-byte sector (stride 2 lines)
+    LLLine* ll_diag;               // [2][16] diagonal-row snapshot (owner -> everybody when G <= 16, -> reducers otherwise)
+    LLLine* ll_tot;                // [2][QB_MAXG][2][16] per-reader copies of {totals, diagonal row} (G > 16)
+    LLLine* ll_bar;                // [2][QB_MAXG]
+    LLLine* ll_res;                // [2][QB_NV]
+    double* wpart;                 // [G][QB_NV]
+    uint32_t epoch_base;           // unique per launch within one factorisation, > 0
+    long long* prof;               // debug (PLA_QR_PROF=1): [G][QB_NPROF] cycles per phase of thread 0, or null
+};
+constexpr int QB_NPROF = 12;
+#define QB_T(i) do { if (p.prof != nullptr && threadIdx.x == 0) { const long long now_ = clock64(); \
+                     pacc[i] += now_ - plast; plast = now_; } } while (0)
+
+__global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const BlockParams p) {
+    extern __shared__ __align__(16) double qb_smem[];
+    double* P = qb_smem;                                   // [rpc][QB_LDP]  block slice, row-major
+    double* Vs = P + (size_t)p.rpc * QB_LDP;               // [rpc][16]      reflectors of the current sub-panel
+    double* Ws = Vs + (size_t)p.rpc * QR_NB;               // [16][QB_WLD]   W totals, then W2 in place
+    double* Gs = Ws + QR_NB * QB_WLD;                      // [16][16]       Gram of the sub-panel's reflectors
+    double* red = Gs + QR_NB * QR_NB;                      // [16]           totals of the column step
+    double* drow = red + QR_NB;                            // [16]           snapshot of the diagonal row
+    double* wsum = drow + QR_NB;                           // [8][16]
+    double* taus = wsum + (QB_THREADS / 32) * QR_NB;       // [16]
+    double* rsum = taus + QR_NB;                           // [9]  warp sums of a reducer + the diagonal entry
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x, b = blockIdx.x, JB = p.JB, rpc = p.rpc;
+    const long long rows = p.M - p.J0;
+    const long long l0 = (long long)b * rpc;               // block-local index of my first row
+    const int nloc = (int)max(0LL, min((long long)rpc, rows - l0));
+    const int nit = rpc / QR_NB;                           // row sweeps of the 16 x 16 thread grid
+    double* Ablk = p.A + p.J0 * p.lda + p.J0;
+    long long pacc[QB_NPROF], plast = clock64();
+#pragma unroll
+    for (int i = 0; i < QB_NPROF; ++i) pacc[i] = 0;
+
+    for (int idx = tid; idx < nloc * QR_NBO; idx += QB_THREADS) {
+        const int r = idx >> 7, c = idx & (QR_NBO - 1);
+        P[r * QB_LDP + c] = (c < JB) ? Ablk[(l0 + r) * p.lda + c] : 0.0;
+    }
     __syncthreads();
-    for (int j = 0; j < JB; ++j) {
-        gcol[r] = (r < j) ? G[(size_t)r * QR_NBO + j] : 0.0;
-        __syncthreads();
-        const double tj = tau[j];
-        if (r < j) {
-            double sacc = 0.0;
-            for (int l = r; l < j; ++l) sacc = fma(Ts[r * (QR_NBO + 1) + l], gcol[l], sacc);
-            Ts[r * (QR_NBO + 1) + j] = -tj * sacc;
-        } else if (r == j) {
-            Ts[j * (QR_NBO + 1) + j] = tj;
+    QB_T(0);
+
+    const int c = tid & 15, g = tid >> 4;                  // column of the sub-panel / row group
+    for (int c0 = 0; c0 < JB; c0 += QR_NB) {
+        const int jbp = min(QR_NB, JB - c0);
+        // ---- partial sums for the first column of the sub-panel
+        double part = 0.0;
+        for (int it = 0; it < nit; ++it) {
+            const int r = g + QR_NB * it;
+            if (r < nloc && l0 + r > c0 && c < jbp) part = fma(P[r * QB_LDP + c0], P[r * QB_LDP + c0 + c], part);
+        }
+        for (int j = 0; j < jbp; ++j) {
+            const int gc = c0 + j;                         // block-local column == block-local diagonal row
+            const uint32_t epoch = p.epoch_base + (uint32_t)gc;
+            const int par = (int)(epoch & 1u);
+            // The column step is written without intra-warp divergence (uniform loops closed by warp votes, PTX-
+            // predicated stores): a divergent spin / single-thread block in warp 0 cost ~7000 cycles per column
+            // on B200 (measured with clock64 around the first shared-memory read after it).
+            // (1) CTA totals of the 16 quantities, published as LL lines
+            part += __shfl_xor_sync(0xffffffffu, part, 16);
+            st_shared_pred(wsum + wid * QR_NB + (lane & 15), part, lane < QR_NB);
+            __syncthreads();
+            if (wid == 0) {                                  // warp-uniform
+                const int q = lane & 15;
+                const bool act = lane < QR_NB && q >= j && q < jbp;
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < QB_THREADS / 32; ++w) tot += wsum[w * QR_NB + q];
+                ll_store(p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + b), tot, epoch, act);
+                const bool own = gc >= l0 && gc < l0 + nloc;     // I own the diagonal row: publish its snapshot
+                const double dv = P[(own ? (int)(gc - l0) : 0) * QB_LDP + c0 + q];
+                ll_store(p.ll_diag + par * QR_NB + q, dv, epoch, act && own);
+            }
+            QB_T(1);
+            // (2) exchange.  Few CTAs (G <= 16): all-to-all, every CTA reads the G partials of each quantity (one line
+            //     per thread) and sums them in the same fixed order.  Many CTAs: all-to-all polling traffic grows as
+            //     16 G^2 lines per column and saturates the L2 slices (measured: ~5000 cycles per column at G = 86),
+            //     so quantity q is summed by ONE CTA (q mod G), which publishes the total; everybody reads 16 totals.
+            if (G <= QR_NB) {
+                const int q = tid >> 4, slot = tid & 15;
+                const bool act = q >= j && q < jbp && slot < G;
+                const LLLine* line = p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + (slot < G ? slot : 0));
+                double acc = 0.0;
+                bool ok;
+                do {
+                    ok = ll_try_load(line, epoch, acc) || !act;
+                } while (!__all_sync(0xffffffffu, ok));
+                if (!act) acc = 0.0;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                st_shared_pred(red + q, acc, slot == 0);
+            } else {
+                for (int q = j; q < jbp; ++q) {
+                    if (q % G != b) continue;                 // CTA-uniform: I am the reducer of quantity q
+                    // thread t < G polls the partial of CTA t (private sector), thread G the diagonal-row entry
+                    const bool act = tid <= G;
+                    const LLLine* line = tid < G ? p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + tid)
+                                                 : p.ll_diag + par * QR_NB + q;
+                    double val = 0.0;
+                    bool ok;
+                    do {
+                        ok = ll_try_load(line, epoch, val) || !act;
+                    } while (!__all_sync(0xffffffffu, ok));
+                    st_shared_pred(rsum + 8, val, tid == G);               // the diagonal entry is passed through
+                    if (tid >= G) val = 0.0;
+                    val = warp_sum(val);
+                    st_shared_pred(rsum + wid, val, lane == 0);
+                    __syncthreads();
+                    double tot = 0.0;
+#pragma unroll
+                    for (int w = 0; w < QB_THREADS / 32; ++w) tot += rsum[w];
+                    // one private copy per reader: a polled line then has exactly one writer and one reader
+                    LLLine* dst = p.ll_tot + ((size_t)(par * QB_MAXG + (tid < G ? tid : 0))) * 2 * QR_NB + q;
+                    ll_store(dst, tot, epoch, tid < G);
+                    ll_store(dst + QR_NB, rsum[8], epoch, tid < G);
+                    __syncthreads();
+                }
+            }
+            if (wid == 0) {
+                // warp-uniform: lanes 0..15 fetch the totals (many-CTA scheme), lanes 16..31 the diagonal-row snapshot
+                const int qd = lane & 15;
+                const bool is_tot = lane < QR_NB;
+                const bool need = qd >= j && qd < jbp && (!is_tot || G > QR_NB);
+                const LLLine* line = G > QR_NB ? p.ll_tot + ((size_t)(par * QB_MAXG + b)) * 2 * QR_NB + lane
+                                               : p.ll_diag + par * QR_NB + qd;
+                double dv = 0.0;
+                bool ok;
+                do {
+                    ok = ll_try_load(line, epoch, dv) || !need;
+                } while (!__all_sync(0xffffffffu, ok));
+                st_shared_pred((is_tot ? red : drow) + qd, dv, need);
+            }
+            __syncthreads();
+            QB_T(2);
+            // (3) reflector j (LAPACK dlarfg), computed redundantly (and bit-identically) by every thread
+            const double sigma = red[j], alpha = drow[j];
+            double beta = alpha, tau = 0.0, scale = 0.0;
+            if (sigma != 0.0) {
+                const double nrm = sqrt(fma(alpha, alpha, sigma));
+                beta = alpha >= 0.0 ? -nrm : nrm;
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            st_shared_pred(taus + j, tau, tid == 0);
+            st_global_pred(p.tau + gc, tau, tid == 0 && b == 0);
+            const double wv_c = (c > j && c < jbp) ? tau * fma(scale, red[c], drow[c]) : 0.0;
+            const double wv_n = (j + 1 < jbp) ? tau * fma(scale, red[j + 1], drow[j + 1]) : 0.0;
+            QB_T(10);
+            // (4) apply to my rows; gather the partial sums of column j + 1 on the fly
+            part = 0.0;
+            for (int it0 = 0; it0 < nit; it0 += 4) {           // 4 row sweeps per batch: 12 shared-memory loads in flight
+                double aj[4], an[4], ac[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = g + QR_NB * (it0 + u);
+                    const bool valid = it0 + u < nit && r < nloc;
+                    const double* row = P + (valid ? r : 0) * QB_LDP + c0;
+                    aj[u] = valid ? row[j] : 0.0;
+                    an[u] = (valid && j + 1 < jbp) ? row[j + 1] : 0.0;
+                    ac[u] = valid ? row[c] : 0.0;
+                }
+                __syncwarp();                               // every lane has read the old rows before anyone writes
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = g + QR_NB * (it0 + u);
+                    const bool valid = it0 + u < nit && r < nloc;
+                    const long long li = l0 + r;
+                    double* row = P + (valid ? r : 0) * QB_LDP + c0;
+                    if (valid && li >= gc) {
+                        if (li == gc) {
+                            if (c == j) row[c] = beta;
+                            else if (c > j && c < jbp) row[c] = ac[u] - wv_c;
+                        } else {
+                            const double v = aj[u] * scale;
+                            if (c == j) {
+                                row[c] = v;
+                            } else if (c > j && c < jbp) {
+                                const double anew = fma(-v, wv_c, ac[u]);
+                                row[c] = anew;
+                                if (li > gc + 1) {
+                                    const double x = (c == j + 1) ? anew : fma(-v, wv_n, an[u]);
+                                    part = fma(x, anew, part);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            QB_T(11);
+            __syncthreads();
+            QB_T(3);
+        }
+        if (tid >= jbp && tid < QR_NB) taus[tid] = 0.0;
+
+        // ---- the rest of the block: C <- (I - V T^T V^T) C
+        const int cs = c0 + jbp;                           // first remaining column
+        const int ncb = JB - cs;
+        if (ncb <= 0) break;
+        const uint32_t epoch = p.epoch_base + (uint32_t)(c0 / QR_NB) + 1u;   // sub-panel index (own buffers)
+        const int par = (int)(epoch & 1u);
+        for (int idx = tid; idx < rpc * QR_NB; idx += QB_THREADS) {
+            const int r = idx >> 4, k = idx & 15;
+            const long long li = l0 + r;
+            const int dk = c0 + k;
+            double v = 0.0;
+            if (r < nloc && k < jbp) v = li > dk ? P[r * QB_LDP + dk] : (li == dk ? 1.0 : 0.0);
+            Vs[idx] = v;
         }
         __syncthreads();
+        double* mypart = p.wpart + (size_t)b * QB_NV;
+        {   // W partial: thread <-> (column pair, 4 of the 16 reflectors), all my rows
+            const int cp = tid & 63, kq = tid >> 6;
+            const int ca = cp < QB_WLD / 2 ? cp : QB_WLD, cb = ca + QB_WLD / 2;     // columns cp and cp + 56
+            double acc[4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = 0.0;
+            if (ca < ncb && l0 + nloc > c0) {
+                const bool hb = cb < ncb;
+                for (int r = 0; r < nloc; ++r) {
+                    const double xa = P[r * QB_LDP + cs + ca];
+                    const double xb = hb ? P[r * QB_LDP + cs + cb] : 0.0;
+                    const double2 v01 = *reinterpret_cast<const double2*>(Vs + r * QR_NB + 4 * kq);
+                    const double2 v23 = *reinterpret_cast<const double2*>(Vs + r * QR_NB + 4 * kq + 2);
+                    acc[0][0] = fma(v01.x, xa, acc[0][0]); acc[0][1] = fma(v01.x, xb, acc[0][1]);
+                    acc[1][0] = fma(v01.y, xa, acc[1][0]); acc[1][1] = fma(v01.y, xb, acc[1][1]);
+                    acc[2][0] = fma(v23.x, xa, acc[2][0]); acc[2][1] = fma(v23.x, xb, acc[2][1]);
+                    acc[3][0] = fma(v23.y, xa, acc[3][0]); acc[3][1] = fma(v23.y, xb, acc[3][1]);
+                }
+            }
+            if (ca < QB_WLD) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mypart[(4 * kq + k) * QB_WLD + ca] = acc[k][0];
+                    mypart[(4 * kq + k) * QB_WLD + cb] = acc[k][1];
+                }
+            }
+            // Gram partial: thread <-> (i, jj), i < jj
+            const int gi = tid >> 4, gj = tid & 15;
+            double gacc = 0.0;
+            if (gi < gj && gj < jbp && l0 + nloc > c0)
+                for (int r = 0; r < nloc; ++r) gacc = fma(Vs[r * QR_NB + gi], Vs[r * QR_NB + gj], gacc);
+            mypart[QR_NB * QB_WLD + tid] = gacc;
+        }
+        QB_T(4);
+        // flag barrier: my partial is visible before my flag
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) ll_store(p.ll_bar + par * QB_MAXG + b, 0.0, epoch);
+        if (tid < G) (void)ll_load(p.ll_bar + par * QB_MAXG + tid, epoch);
+        __syncthreads();
+        __threadfence();
+        QB_T(5);
+        {   // my slice of the sums over CTAs: 8 threads per value, fixed order
+            const int S = (QB_NV + G - 1) / G;
+            const int e = tid >> 3, p8 = tid & 7;
+            for (int e0 = 0; e0 < S; e0 += QB_THREADS / 8) {
+                const int idx = b * S + e0 + e;
+                const bool ok = (e0 + e < S) && idx < QB_NV;
+                double acc = 0.0;
+                if (ok) {
+                    for (int bb = p8; bb < G; bb += 32) {
+                        double t[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int b2 = bb + 8 * u;
+                            t[u] = b2 < G ? __ldcg(p.wpart + (size_t)b2 * QB_NV + idx) : 0.0;
+                        }
+                        acc += (t[0] + t[1]) + (t[2] + t[3]);
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (ok && p8 == 0) ll_store(p.ll_res + (size_t)par * QB_NV + idx, acc, epoch);
+            }
+        }
+        QB_T(6);
+        // all-gather of the totals (only the entries in use are polled; all of a thread's lines in flight at once)
+        {
+            const LLLine* resl = p.ll_res + (size_t)par * QB_NV;
+            double v[QB_NV / QB_THREADS];
+            unsigned pending = 0;
+#pragma unroll
+            for (int i = 0; i < QB_NV / QB_THREADS; ++i) {
+                const int idx = tid + QB_THREADS * i;
+                bool need;
+                if (idx < QR_NB * QB_WLD) {
+                    const int k = idx / QB_WLD, cc = idx - k * QB_WLD;
+                    need = k < jbp && cc < ncb;
+                } else {
+                    const int e = idx - QR_NB * QB_WLD, gi = e >> 4, gj = e & 15;
+                    need = gi < gj && gj < jbp;
+                }
+                v[i] = 0.0;
+                if (need) pending |= 1u << i;
+            }
+            do {
+#pragma unroll
+                for (int g4 = 0; g4 < QB_NV / QB_THREADS / 4; ++g4) {
+                    unsigned long long w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+                    const unsigned m4 = (pending >> (4 * g4)) & 15u;
+                    ll_load4<QB_THREADS * (int)sizeof(LLLine)>(resl + tid + 4 * QB_THREADS * g4, m4, w0, w1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double val;
+                        const bool got = ll_ready(w0[i], w1[i], epoch, val) && ((m4 >> i) & 1u);
+                        if (got) { v[4 * g4 + i] = val; pending &= ~(1u << (4 * g4 + i)); }
+                    }
+                }
+            } while (__any_sync(0xffffffffu, pending != 0));
+#pragma unroll
+            for (int i = 0; i < QB_NV / QB_THREADS; ++i) {
+                const int idx = tid + QB_THREADS * i;
+                if (idx < QR_NB * QB_WLD) Ws[idx] = v[i];
+                else Gs[idx - QR_NB * QB_WLD] = v[i];
+            }
+        }
+        __syncthreads();
+        QB_T(7);
+        if (tid < ncb) {                                   // W2 = T^T W by forward substitution, one column per thread
+            double w2[QR_NB];
+#pragma unroll
+            for (int k = 0; k < QR_NB; ++k) {
+                double sacc = (k < jbp) ? Ws[k * QB_WLD + tid] : 0.0;
+#pragma unroll
+                for (int l = 0; l < k; ++l) sacc = fma(-Gs[l * QR_NB + k], w2[l], sacc);
+                w2[k] = taus[k] * sacc;
+            }
+#pragma unroll
+            for (int k = 0; k < QR_NB; ++k) Ws[k * QB_WLD + tid] = w2[k];
+        }
+        __syncthreads();
+        {   // C -= V W2: thread <-> (column pair, every 4th row)
+            const int cp = tid & 63, rq = tid >> 6;
+            const int ca = cp < QB_WLD / 2 ? cp : QB_WLD, cb = ca + QB_WLD / 2;
+            if (ca < ncb && l0 + nloc > c0) {
+                const bool hb = cb < ncb;
+                double wa[QR_NB], wb[QR_NB];
+#pragma unroll
+                for (int k = 0; k < QR_NB; ++k) { wa[k] = Ws[k * QB_WLD + ca]; wb[k] = hb ? Ws[k * QB_WLD + cb] : 0.0; }
+                for (int r = rq; r < nloc; r += 4) {
+                    if (l0 + r < c0) continue;
+                    const double2* v2 = reinterpret_cast<const double2*>(Vs + r * QR_NB);
+                    double sa = 0.0, sb = 0.0;
+#pragma unroll
+                    for (int k = 0; k < QR_NB / 2; ++k) {
+                        const double2 vv = v2[k];
+                        sa = fma(vv.x, wa[2 * k], sa); sb = fma(vv.x, wb[2 * k], sb);
+                        sa = fma(vv.y, wa[2 * k + 1], sa); sb = fma(vv.y, wb[2 * k + 1], sb);
+                    }
+                    P[r * QB_LDP + cs + ca] -= sa;
+                    if (hb) P[r * QB_LDP + cs + cb] -= sb;
+                }
+            }
+        }
+        __syncthreads();
+        QB_T(8);
     }
-    for (int c = 0; c < QR_NBO; ++c) T[(size_t)r * QR_NBO + c] = Ts[r * (QR_NBO + 1) + c];
+    __syncthreads();
+    // ---- write the factored block back, and the explicit reflectors for the tensor-core update
+    for (int idx = tid; idx < nloc * QR_NBO; idx += QB_THREADS) {
+        const int r = idx >> 7, cc = idx & (QR_NBO - 1);
+        const long long li = l0 + r;
+        const double v = P[r * QB_LDP + cc];
+        if (cc < JB) Ablk[li * p.lda + cc] = v;
+        if (p.Vx != nullptr) p.Vx[li * QR_NBO + cc] = (cc < JB) ? (li > cc ? v : (li == cc ? 1.0 : 0.0)) : 0.0;
+    }
+    QB_T(9);
+    if (p.prof != nullptr && tid == 0)
+        for (int i = 0; i < QB_NPROF; ++i) p.prof[(size_t)b * QB_NPROF + i] = pacc[i];
+}
+
+// W2 = op(T) W for the compact-WY factor of a block of <= 128 reflectors, T given implicitly by the Gram matrix
+// Gm = V^T V and tau:  T^{-1} = striu(Gm) + diag(1 / tau).  Forward substitution gives T^T W (QR: apply H_k ... H_1),
+// backward substitution T W (forming Q).  One thread per column of W, blocked by 16 rows; the 1/tau of the diagonal
+// turns into a multiplication, so tau = 0 (H = I) needs no special case.  Replaces forming T (dlarft) + a GEMM.
+constexpr int QW_THREADS = 64;
+__global__ void __launch_bounds__(QW_THREADS) qr_w2_kernel(const double* __restrict__ Gm, const double* __restrict__ tau,
+                                                           int JB, const double* __restrict__ W, long long ldw,
+                                                           long long nc, double* __restrict__ W2, long long ldw2,
+                                                           int transpose) {
+    extern __shared__ __align__(16) double qw_smem[];
+    double* Hs = qw_smem;                          // [128][128]: Hs[a][e] = coefficient of w2_a in equation e
+    double* w2s = Hs + QR_NBO * QR_NBO;            // [128][QW_THREADS]
+    double* ts = w2s + QR_NBO * QW_THREADS;        // [128]
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < QR_NBO * QR_NBO; idx += QW_THREADS) {
+        const int a = idx >> 7, e = idx & (QR_NBO - 1);
+        double v = 0.0;
+        if (a < JB && e < JB) v = transpose ? (a < e ? Gm[idx] : 0.0) : (a > e ? Gm[e * QR_NBO + a] : 0.0);
+        Hs[idx] = v;
+    }
+    for (int idx = tid; idx < QR_NBO; idx += QW_THREADS) ts[idx] = idx < JB ? tau[idx] : 0.0;
+    __syncthreads();
+    const long long col = (long long)blockIdx.x * QW_THREADS + tid;
+    if (col >= nc) return;
+    const int nblk = (JB + QR_NB - 1) / QR_NB;
+    for (int qi = 0; qi < nblk; ++qi) {
+        const int q = transpose ? qi : nblk - 1 - qi;      // equations of block q
+        double acc[QR_NB];
+#pragma unroll
+        for (int kk = 0; kk < QR_NB; ++kk) {
+            const int k = QR_NB * q + kk;
+            acc[kk] = k < JB ? W[(long long)k * ldw + col] : 0.0;
+        }
+        for (int pi = 0; pi < qi; ++pi) {                  // blocks already solved
+            const int pb = transpose ? pi : nblk - 1 - pi;
+            for (int l = 0; l < QR_NB; ++l) {
+                const double w = w2s[(QR_NB * pb + l) * QW_THREADS + tid];
+                const double2* h2 = reinterpret_cast<const double2*>(Hs + (QR_NB * pb + l) * QR_NBO + QR_NB * q);
+#pragma unroll
+                for (int kk = 0; kk < QR_NB / 2; ++kk) {
+                    const double2 h = h2[kk];
+                    acc[2 * kk] = fma(-h.x, w, acc[2 * kk]);
+                    acc[2 * kk + 1] = fma(-h.y, w, acc[2 * kk + 1]);
+                }
+            }
+        }
+        double w2[QR_NB];
+        if (transpose) {
+#pragma unroll
+            for (int kk = 0; kk < QR_NB; ++kk) {
+                double sacc = acc[kk];
+#pragma unroll
+                for (int l = 0; l < kk; ++l) sacc = fma(-Hs[(QR_NB * q + l) * QR_NBO + QR_NB * q + kk], w2[l], sacc);
+                w2[kk] = ts[QR_NB * q + kk] * sacc;
+            }
+        } else {
+#pragma unroll
+            for (int kk = QR_NB - 1; kk >= 0; --kk) {
+                double sacc = acc[kk];
+#pragma unroll
+                for (int l = QR_NB - 1; l > kk; --l) sacc = fma(-Hs[(QR_NB * q + l) * QR_NBO + QR_NB * q + kk], w2[l], sacc);
+                w2[kk] = ts[QR_NB * q + kk] * sacc;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < QR_NB; ++kk) {
+            const int k = QR_NB * q + kk;
+            w2s[k * QW_THREADS + tid] = w2[kk];
+            W2[(long long)k * ldw2 + col] = w2[kk];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -573,7 +1077,10 @@ struct QrWs {
     // outer (BLAS-3) level
     double* Vx;              // (M) x 128   explicit block reflector
     double* Gbig;            // 128 x 128
-    double* Tbig;            // 128 x 128
+    LLLine* ll;              // LL lines of the cooperative block kernel: step | diag | bar | res
+    size_t ll_bytes;
+    double* cpart;           // [QB_MAXG][QB_NV] reduce-scatter partials
+    long long* prof;         // [QB_MAXG][QB_NPROF] debug cycle counters
     double* Wbig;            // 128 x N
     double* W2big;           // 128 x N
     void* gemm_ws; size_t gemm_ws_bytes;
@@ -595,7 +1102,10 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
     const size_t o_w2s = take((size_t)QR_NB * (size_t)(N > 0 ? N : 1) * 8);
     const size_t o_vx = take((size_t)M * QR_NBO * 8);
     const size_t o_gb = take((size_t)QR_NBO * QR_NBO * 8);
-    const size_t o_tb = take((size_t)QR_NBO * QR_NBO * 8);
+    const size_t ll_lines = (size_t)4 * QR_NB * QB_MAXG + 2 * QR_NB + (size_t)4 * QB_MAXG * QR_NB + 2 * QB_MAXG + 2 * QB_NV;
+    const size_t o_ll = take(ll_lines * sizeof(LLLine));
+    const size_t o_cp = take((size_t)QB_MAXG * QB_NV * 8);
+    const size_t o_pf = take((size_t)QB_MAXG * QB_NPROF * 8);
     const size_t o_wb = take((size_t)QR_NBO * (size_t)N * 8);
     const size_t o_w2 = take((size_t)QR_NBO * (size_t)N * 8);
     // split-K partials of the block-reflector GEMMs: at most 64 splits of a 128 x nc tile row (nc <= N)
@@ -613,7 +1123,10 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
         out->max_splits = max_splits;
         out->Vx = (double*)(b + o_vx);
         out->Gbig = (double*)(b + o_gb);
-        out->Tbig = (double*)(b + o_tb);
+        out->ll = (LLLine*)(b + o_ll);
+        out->ll_bytes = ll_lines * sizeof(LLLine);
+        out->cpart = (double*)(b + o_cp);
+        out->prof = (long long*)(b + o_pf);
         out->Wbig = (double*)(b + o_wb);
         out->W2big = (double*)(b + o_w2);
         out->gemm_ws = (void*)(b + o_gw);
@@ -705,36 +1218,82 @@ using namespace pla;
 
 extern "C" size_t pla_qr_workspace_bytes(int64_t M, int64_t N) { return qr_ws_layout(M, N, nullptr, nullptr); }
 
-// Build Vx (explicit reflectors J0 .. J0+JB-1) and the compact-WY factor Tbig of the whole block.
-static int build_block_reflector(const double* A, long long lda, long long M, long long J0, int JB,
-                                 const double* tau, const QrWs& w, cudaStream_t st) {
+// Cooperative factorisation of the block (J0, JB); returns 1 when the block does not fit (caller falls back).
+static int run_block_coop(double* A, long long lda, long long M, long long J0, int JB, double* tau, const QrWs& w,
+                          uint32_t epoch_base, cudaStream_t st) {
+    static const int target = [] { const char* e = getenv("PLA_QR_RPC"); int v = e ? atoi(e) : 96; return v < 16 ? 96 : v; }();
     const long long rows = M - J0;
-    int nb = (int)((rows * QR_NBO + 255) / 256);
-    if (nb > 8 * num_sms()) nb = 8 * num_sms();
-    qr_form_v_kernel<<<nb, 256, 0, st>>>(A, lda, M, J0, JB, w.Vx);
-    PLA_LAUNCH_CHECK();
-    int rc = pla_gemm_f64(1, 0, QR_NBO, QR_NBO, rows, 1.0, w.Vx, QR_NBO, w.Vx, QR_NBO, 0.0, w.Gbig, QR_NBO,
-                          w.gemm_ws, w.gemm_ws_bytes, st);
-    if (rc) return rc;
-    const size_t smem = (size_t)(QR_NBO * (QR_NBO + 1) + QR_NBO) * sizeof(double);
-    PLA_CUDA(cudaFuncSetAttribute(qr_build_tbig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    qr_build_tbig_kernel<<<1, QR_NBO, smem, st>>>(w.Gbig, tau + J0, JB, w.Tbig);
-    PLA_LAUNCH_CHECK();
+    const int sms = num_sms() < QB_MAXG ? num_sms() : QB_MAXG;
+    long long G = (rows + target - 1) / target;
+    if (G > sms) G = sms;
+    if (G < 1) G = 1;
+    long long rpc = (rows + G - 1) / G;
+    rpc = (rpc + QR_NB - 1) / QR_NB * QR_NB;
+    if (rpc > QB_RPC_MAX) return 1;
+    G = (rows + rpc - 1) / rpc;
+    BlockParams bp;
+    bp.A = A; bp.lda = lda; bp.M = M; bp.J0 = J0; bp.JB = JB; bp.tau = tau + J0; bp.Vx = w.Vx; bp.rpc = (int)rpc;
+    bp.ll_step = w.ll;
+    bp.ll_diag = bp.ll_step + (size_t)4 * QR_NB * QB_MAXG;
+    bp.ll_tot = bp.ll_diag + 2 * QR_NB;
+    bp.ll_bar = bp.ll_tot + (size_t)4 * QB_MAXG * QR_NB;
+    bp.ll_res = bp.ll_bar + 2 * QB_MAXG;
+    bp.wpart = w.cpart;
+    bp.epoch_base = epoch_base;
+    static const bool prof = [] { const char* e = getenv("PLA_QR_PROF"); return e && e[0] == '1'; }();
+    bp.prof = prof ? w.prof : nullptr;
+    const size_t smem = ((size_t)rpc * QB_LDP + (size_t)rpc * QR_NB + QR_NB * QB_WLD + QR_NB * QR_NB + 3 * QR_NB +
+                         (QB_THREADS / 32) * QR_NB + QB_THREADS / 32 + 2) * sizeof(double);
+    PLA_CUDA(cudaFuncSetAttribute(qr_block_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {(void*)&bp};
+    PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_block_coop_kernel, dim3((unsigned)G), dim3(QB_THREADS), args,
+                                         smem, st));
+    note_launch();
+    if (prof) {      // debug only: synchronises
+        static const char* names[QB_NPROF] = {"load", "publish", "gather", "apply", "Wpart", "barrier", "slice", "allgather",
+                                              "W2+update", "store", "scalars", "applyloop"};
+        long long h[QB_MAXG * QB_NPROF];
+        PLA_CUDA(cudaStreamSynchronize(st));
+        PLA_CUDA(cudaMemcpy(h, w.prof, (size_t)G * QB_NPROF * 8, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "qr_block_coop J0=%lld rows=%lld G=%lld rpc=%lld | kcycles (CTA0 / max):", J0, rows, G, rpc);
+        for (int i = 0; i < QB_NPROF; ++i) {
+            long long mx = 0;
+            for (int g2 = 0; g2 < G; ++g2) mx = h[g2 * QB_NPROF + i] > mx ? h[g2 * QB_NPROF + i] : mx;
+            fprintf(stderr, " %s %.1f/%.1f", names[i], h[i] / 1e3, mx / 1e3);
+        }
+        fprintf(stderr, "\n");
+    }
     return 0;
 }
 
-// C[J0:M, 0:nc] <- (I - Vx op(Tbig) Vx^T) C  with three DMMA GEMMs
-static int apply_block_reflector(long long M, long long J0, double* C, long long ldc, long long nc, int t_transpose,
+// Explicit reflectors Vx of block (J0, JB) (unless the cooperative kernel already wrote them) and their Gram matrix.
+static int build_block_reflector(const double* A, long long lda, long long M, long long J0, int JB, bool have_vx,
                                  const QrWs& w, cudaStream_t st) {
+    const long long rows = M - J0;
+    if (!have_vx) {
+        int nb = (int)((rows * QR_NBO + 255) / 256);
+        if (nb > 8 * num_sms()) nb = 8 * num_sms();
+        qr_form_v_kernel<<<nb, 256, 0, st>>>(A, lda, M, J0, JB, w.Vx);
+        PLA_LAUNCH_CHECK();
+    }
+    return pla_gemm_f64(1, 0, QR_NBO, QR_NBO, rows, 1.0, w.Vx, QR_NBO, w.Vx, QR_NBO, 0.0, w.Gbig, QR_NBO,
+                        w.gemm_ws, w.gemm_ws_bytes, st);
+}
+
+// C[J0:M, 0:nc] <- (I - Vx op(T) Vx^T) C: two DMMA GEMMs around the substitution kernel (T never formed)
+static int apply_block_reflector(long long M, long long J0, int JB, const double* tau, double* C, long long ldc,
+                                 long long nc, int t_transpose, const QrWs& w, cudaStream_t st) {
     if (nc <= 0) return 0;
     const long long rows = M - J0;
     double* Crows = C + J0 * ldc;
     int rc = pla_gemm_f64(1, 0, QR_NBO, nc, rows, 1.0, w.Vx, QR_NBO, Crows, ldc, 0.0, w.Wbig, nc, w.gemm_ws,
                           w.gemm_ws_bytes, st);                                   // W = Vx^T C
     if (rc) return rc;
-    rc = pla_gemm_f64(t_transpose ? 1 : 0, 0, QR_NBO, nc, QR_NBO, 1.0, w.Tbig, QR_NBO, w.Wbig, nc, 0.0, w.W2big, nc,
-                      w.gemm_ws, w.gemm_ws_bytes, st);                            // W2 = op(T) W
-    if (rc) return rc;
+    const size_t smem = ((size_t)QR_NBO * QR_NBO + (size_t)QR_NBO * QW_THREADS + QR_NBO) * sizeof(double);
+    PLA_CUDA(cudaFuncSetAttribute(qr_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qr_w2_kernel<<<(unsigned)((nc + QW_THREADS - 1) / QW_THREADS), QW_THREADS, smem, st>>>(
+        w.Gbig, tau + J0, JB, w.Wbig, nc, nc, w.W2big, nc, t_transpose);          // W2 = op(T) W
+    PLA_LAUNCH_CHECK();
     return pla_gemm_f64(0, 0, rows, nc, QR_NBO, -1.0, w.Vx, QR_NBO, w.W2big, nc, 1.0, Crows, ldc, w.gemm_ws,
                         w.gemm_ws_bytes, st);                                     // C -= Vx W2
 }
@@ -750,22 +1309,37 @@ extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64
     QrWs w;
     qr_ws_layout(M, N, ws, &w);
     cudaStream_t st = (cudaStream_t)stream;
-    for (long long J0 = 0; J0 < ncols_factor; J0 += QR_NBO) {
+    static const bool use_coop = [] { const char* e = getenv("PLA_QR_COOP"); return !(e && e[0] == '0'); }();
+    bool ll_clean = false;
+    uint32_t blk = 0;
+    for (long long J0 = 0; J0 < ncols_factor; J0 += QR_NBO, ++blk) {
         const int JB = (int)((ncols_factor - J0) < QR_NBO ? (ncols_factor - J0) : QR_NBO);
-        // inner level: 16-column panels; their reflectors are applied only inside this block
-        for (long long j0 = J0; j0 < J0 + JB; j0 += QR_NB) {
-            const int jb = (int)((J0 + JB - j0) < QR_NB ? (J0 + JB - j0) : QR_NB);
-            int rc = run_panel(A, lda, M, j0, jb, tau, w, st);
-            if (rc) return rc;
-            rc = run_trailing(A, lda, M, j0, jb, A + j0 + jb, lda, (J0 + JB) - (j0 + jb), /*T^T*/ 1, w, st);
-            if (rc) return rc;
+        const long long nc = N - (J0 + JB);
+        bool done = false;
+        if (use_coop) {
+            if (!ll_clean) {                 // epochs restart with every factorisation: stale lines must not match
+                PLA_CUDA(cudaMemsetAsync(w.ll, 0, w.ll_bytes, st));
+                ll_clean = true;
+            }
+            const int rc = run_block_coop(A, lda, M, J0, JB, tau, w, (blk + 1u) * 256u, st);
+            if (rc < 0 || rc > 1) return rc;
+            done = (rc == 0);
+        }
+        if (!done) {
+            // inner level: 16-column panels; their reflectors are applied only inside this block
+            for (long long j0 = J0; j0 < J0 + JB; j0 += QR_NB) {
+                const int jb = (int)((J0 + JB - j0) < QR_NB ? (J0 + JB - j0) : QR_NB);
+                int rc = run_panel(A, lda, M, j0, jb, tau, w, st);
+                if (rc) return rc;
+                rc = run_trailing(A, lda, M, j0, jb, A + j0 + jb, lda, (J0 + JB) - (j0 + jb), /*T^T*/ 1, w, st);
+                if (rc) return rc;
+            }
         }
         // outer level: the whole block reflector hits the remaining columns through the tensor cores
-        const long long nc = N - (J0 + JB);
         if (nc > 0) {
-            int rc = build_block_reflector(A, lda, M, J0, JB, tau, w, st);
+            int rc = build_block_reflector(A, lda, M, J0, JB, done, w, st);
             if (rc) return rc;
-            rc = apply_block_reflector(M, J0, A + J0 + JB, lda, nc, /*T^T*/ 1, w, st);
+            rc = apply_block_reflector(M, J0, JB, tau, A + J0 + JB, lda, nc, /*T^T*/ 1, w, st);
             if (rc) return rc;
         }
     }
@@ -790,9 +1364,9 @@ extern "C" int pla_orgqr_f64(const double* A, int64_t M, int64_t K, int64_t lda,
     const long long last = ((K - 1) / QR_NBO) * QR_NBO;
     for (long long J0 = last; J0 >= 0; J0 -= QR_NBO) {
         const int JB = (int)((K - J0) < QR_NBO ? (K - J0) : QR_NBO);
-        int rc = build_block_reflector(A, lda, M, J0, JB, tau, w, st);
+        int rc = build_block_reflector(A, lda, M, J0, JB, false, w, st);
         if (rc) return rc;
-        rc = apply_block_reflector(M, J0, Q + J0, ldq, K - J0, /*T*/ 0, w, st);
+        rc = apply_block_reflector(M, J0, JB, tau, Q + J0, ldq, K - J0, /*T*/ 0, w, st);
         if (rc) return rc;
     }
     return 0;

@@ -14,7 +14,7 @@
 namespace pla {
 
 constexpr int SP_GROUP_MAX = 256;     // consumer threads per group: 256 (8 warps) or, for narrow A, 128
-constexpr int SP_RMAX = 8;            // max rows per tile
+constexpr int SP_RMAX = 16;           // max rows per tile (16 for matrices of <= 256 columns: 32 KB tiles)
 constexpr int SP_MAX_STAGES = 8;
 constexpr int SP_MAX_GROUPS = 4;
 
@@ -22,7 +22,7 @@ constexpr int SP_MAX_GROUPS = 4;
 template <int VEC, int J, int GS> struct SpRows {
     static constexpr int cols = VEC * J * GS;                 // widest matrix this shape serves
     static constexpr int raw = 4096 / cols;                   // rows of a ~32 KB tile
-    static constexpr int capped = raw < 1 ? 1 : (raw > 8 ? 8 : raw);
+    static constexpr int capped = raw < 1 ? 1 : (raw > SP_RMAX ? SP_RMAX : raw);
     static constexpr int value = (VEC == 1 && capped == 1) ? 2 : capped;   // odd n needs an even row count
 };
 
@@ -39,7 +39,7 @@ struct StreamPassParams {
     const int* istop;
     int flags;
     int stages;
-    int use_tma;            // 1: contiguous + 16B aligned rows tiles
+    int use_tma;            // 1: 16B-aligned row tiles -- one bulk copy per tile (lda == n) or per row (lda > n)
     long long ntiles;
 };
 
@@ -95,9 +95,17 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
             double* dst = tiles + (size_t)s * stage_elems;
             const bool tma_ok = p.use_tma && ((elems & 1) == 0);
             if (tma_ok) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(elems * 8));
-                    bulk_g2s(dst, p.A + r0 * p.lda, (uint32_t)(elems * 8), &full[s], pol);
+                if (p.lda == n) {
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(elems * 8));
+                        bulk_g2s(dst, p.A + r0 * p.lda, (uint32_t)(elems * 8), &full[s], pol);
+                    }
+                } else {
+                    // a column block / padded matrix: rows are 16-byte aligned pieces, one bulk copy each
+                    if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(elems * 8));
+                    __syncwarp();
+                    if (lane < rows)
+                        bulk_g2s(dst + (size_t)lane * n, p.A + (r0 + lane) * p.lda, (uint32_t)(n * 8), &full[s], pol);
                 }
             } else {
                 // generic path: strided / unaligned / odd-sized tail tile
@@ -142,16 +150,13 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
         const int rows = (int)min((long long)RT, p.m - r0);
         mbar_wait(&full[s], ph);
         const double* tile = tiles + (size_t)s * stage_elems;
-        double uo[RT], gq[RT];
-#pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            uo[r] = (r < rows && p.u != nullptr) ? ustage[s * SP_RMAX + r] : 0.0;
-            gq[r] = (r < rows && axpy_g) ? gstage[s * SP_RMAX + r] : 0.0;
-        }
+        const double* uo = ustage + s * SP_RMAX;           // old u / g of the tile rows (broadcast reads)
+        const double* gq = gstage + s * SP_RMAX;
+        const bool have_u = p.u != nullptr;
 
         double unew[RT];
         if (do_dot) {
-            double dot[RT];
+            double dot[32];
 #pragma unroll
             for (int r = 0; r < RT; ++r) dot[r] = 0.0;
 #pragma unroll
@@ -173,15 +178,22 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
                     }
                 }
             }
-            // all rows reduced together: RT independent shuffle chains in flight
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int r = 0; r < RT; ++r) dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
             double* myred = gred + (size_t)flip * NW * SP_RMAX;
-            if (lane == 0) {
+            if (RT >= 4) {
+                // many short rows: one multi-value butterfly (2 RT - 1 + ... shuffles instead of 5 RT); lane r ends
+                // up with the warp total of row r
+                warp_multi_sum<RT>(dot);
+                if (lane < RT) myred[wid * SP_RMAX + lane] = dot[0];
+            } else {
+                // all rows reduced together: RT independent shuffle chains in flight
 #pragma unroll
-                for (int r = 0; r < RT; ++r) myred[wid * SP_RMAX + r] = dot[r];
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+                if (lane == 0) {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) myred[wid * SP_RMAX + r] = dot[r];
+                }
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GS) : "memory");
 #pragma unroll
@@ -189,7 +201,8 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
                 double tot = 0.0;
 #pragma unroll
                 for (int k = 0; k < NW; ++k) tot += myred[k * SP_RMAX + r];
-                unew[r] = (su != 0.0) ? fma(sa, tot, su * uo[r]) : sa * tot;     // su == 0: u is write-only (may be uninitialised)
+                const double uold = (r < rows && have_u && su != 0.0) ? uo[r] : 0.0;
+                unew[r] = (su != 0.0) ? fma(sa, tot, su * uold) : sa * tot;     // su == 0: u is write-only (may be uninitialised)
             }
             flip ^= 1;
             if (gt < rows) {
@@ -202,7 +215,7 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < RT; ++r) unew[r] = uo[r];
+            for (int r = 0; r < RT; ++r) unew[r] = (r < rows && have_u) ? uo[r] : 0.0;
             if (gt < rows) {
                 double mine = 0.0;
 #pragma unroll
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
 #pragma unroll
                     for (int r = 0; r < RT; ++r) {
                         if (r < rows) {
-                            const double qv = axpy_g ? gq[r] : unew[r];
+                            const double qv = axpy_g ? gq[r] : unew[r];     // (gq: broadcast read of the staged g)
                             const double* row = tile + (size_t)r * n;
                             if (VEC == 2) {
                                 const double2 a = *reinterpret_cast<const double2*>(row + c);
@@ -285,7 +298,8 @@ static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts
     if (stages < 2) return cudaErrorInvalidValue;
     p.stages = stages;
     p.ntiles = (p.m + RT - 1) / RT;
-    p.use_tma = (p.lda == p.n) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (((size_t)RT * p.n) % 2 == 0);
+    p.use_tma = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
+                (p.lda == p.n ? (((size_t)RT * p.n) % 2 == 0) : (p.n % 2 == 0 && p.lda % 2 == 0));
     int grid = num_sms();
     if ((long long)grid > p.ntiles) grid = (int)p.ntiles;
     *nparts = grid * NG;

@@ -24,6 +24,17 @@ def launch_count():
     return int(_lib.load().pla_launch_count())
 
 
+def note_launches(n):
+    _lib.load().pla_note_launches(int(n))
+
+
+def reserve_pass_workspace(device, n_max):
+    """Allocate the streaming pass's scratch for the CURRENT stream now (so that a CUDA-graph capture on this
+    stream finds it and allocates nothing)."""
+    lib = _lib.load()
+    return Workspace.get(device, lib.pla_stream_pass_workspace_bytes(1, int(n_max)), "pass")
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -88,16 +99,21 @@ def num_sms():
 def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None, flags=PASS_DOT, istop=None):
     """One streaming read of A:  u <- sa*(A w) + su*u ;  z = A^T q ;  zss = [z, |u|^2].
 
-    Returns zss (n+1 doubles).  See pla_stream_pass_f64.
+    Returns zss (n+1 doubles).  See pla_stream_pass_f64.  Matrices wider than PASS_MAX_N columns go through
+    column blocks (two reads of A when both products are requested: z needs the complete u).
     """
     lib = _lib.load()
     A, lda = _rowmajor(A, "A")
     m, n = A.shape
     if zss is None:
         zss = torch.empty(n + 1, dtype=F64, device=A.device)
+    if n > PASS_MAX_N or (n % 2 == 1 and n > PASS_MAX_N // 2):
+        return _stream_pass_wide(A, w, u, g, sc, sa, su, zss, flags, istop)
     nb = lib.pla_stream_pass_workspace_bytes(m, n)
     ws = Workspace.get(A.device, nb, "pass")
     rec = PASS_TIMINGS
+    if rec is not None and torch.cuda.is_current_stream_capturing():
+        rec = None
     if rec is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -107,6 +123,39 @@ def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None,
     if rec is not None:
         e1.record()
         rec.append((int(flags), m, n, e0, e1))
+    return zss
+
+
+WIDE_BLOCK = 4096       # column-block width of the wide-matrix path (even, so every block keeps 16-byte aligned rows)
+
+
+def _stream_pass_wide(A, w, u, g, sc, sa, su, zss, flags, istop):
+    """n > PASS_MAX_N (or odd n > PASS_MAX_N / 2): the per-thread column ownership of the fused kernel does not
+    cover the row, so the products are taken over column blocks A[:, c0:c1] (row tiles of a block are fetched with
+    one bulk copy per row).  u <- sa * sum_k A_k w_k + su * u accumulates over the blocks; z_k = A_k^T q needs the
+    finished u, hence a second sweep when both are requested -- the reference's own two-dgemv formulation
+    (parla/comps/preconditioning.py:30,34).  After LSQR has stopped (``istop`` set) every launch is a no-op."""
+    m, n = A.shape
+    do_dot, do_axpy = bool(flags & PASS_DOT), bool(flags & PASS_AXPY)
+    blocks = [(c0, min(c0 + WIDE_BLOCK, n)) for c0 in range(0, n, WIDE_BLOCK)]
+    tmp = torch.empty(WIDE_BLOCK + 1, dtype=F64, device=A.device)
+    if do_dot:
+        sc_next = None
+        if sc is not None:
+            sc_next = torch.stack((sc[0], torch.ones((), dtype=F64, device=A.device)))
+        for i, (c0, c1) in enumerate(blocks):
+            first = i == 0
+            stream_pass(A[:, c0:c1], w=w[c0:c1], u=u, sc=sc if first else sc_next, sa=sa, su=su if first else 1.0,
+                        zss=tmp[:c1 - c0 + 1], flags=PASS_DOT, istop=istop)
+        if not do_axpy:
+            zss[n:n + 1].copy_(tmp[blocks[-1][1] - blocks[-1][0]:blocks[-1][1] - blocks[-1][0] + 1])
+            return zss
+    if do_axpy:
+        fl = PASS_AXPY | (flags & PASS_AXPY_G)
+        for c0, c1 in blocks:
+            stream_pass(A[:, c0:c1], u=u, g=g, zss=tmp[:c1 - c0 + 1], flags=fl, istop=istop)
+            zss[c0:c1].copy_(tmp[:c1 - c0])
+        zss[n:n + 1].copy_(tmp[blocks[-1][1] - blocks[-1][0]:blocks[-1][1] - blocks[-1][0] + 1])
     return zss
 
 

@@ -78,6 +78,53 @@ def test_stream_pass_strided_and_unaligned(K):
     assert rel(u, u_ref) < 1e-13 and np.linalg.norm(zss[:100] - Aref.T @ u_ref) < 1e-12 * np.linalg.norm(Aref.T @ u_ref)
 
 
+@pytest.mark.parametrize("m,n", [(300, 9000), (257, 16384), (200, 5001), (120, 12289)])
+def test_stream_pass_wide_matrices(K, m, n):
+    """n > 8192 (and odd n > 4096): column-blocked path, every flag combination the drivers use."""
+    rng = np.random.default_rng(n)
+    A, w, u0, gv = rng.standard_normal((m, n)), rng.standard_normal(n), rng.standard_normal(m), rng.standard_normal(m)
+    Ad = dev(A)
+    u = dev(u0)
+    zss = K.stream_pass(Ad, w=dev(w), u=u, sa=0.7, su=-1.3, flags=K.PASS_DOT | K.PASS_AXPY).cpu().numpy()
+    u_ref = 0.7 * (A @ w) + -1.3 * u0
+    assert rel(u, u_ref) < 1e-13
+    assert np.linalg.norm(zss[:n] - A.T @ u_ref) <= 1e-12 * np.linalg.norm(A.T @ u_ref)
+    assert abs(zss[n] - u_ref @ u_ref) <= 1e-13 * (u_ref @ u_ref)
+    y, zss = K.matvec(Ad, dev(w))
+    assert rel(y, A @ w) < 1e-13 and abs(float(zss[n]) - (A @ w) @ (A @ w)) < 1e-13 * ((A @ w) @ (A @ w))
+    zss = K.rmatvec(Ad, dev(u0)).cpu().numpy()
+    assert np.linalg.norm(zss[:n] - A.T @ u0) < 1e-12 * np.linalg.norm(A.T @ u0) and abs(zss[n] - u0 @ u0) < 1e-13 * (u0 @ u0)
+    sc = dev(np.array([-1.0, 1.0]))
+    r = dev(u0)
+    zss = K.stream_pass(Ad, w=dev(w), u=r, g=dev(gv), sc=sc, flags=K.PASS_DOT | K.PASS_AXPY | K.PASS_AXPY_G).cpu().numpy()
+    assert rel(r, u0 - A @ w) < 1e-13 and np.linalg.norm(zss[:n] - A.T @ gv) < 1e-12 * np.linalg.norm(A.T @ gv)
+
+
+def test_stream_pass_column_block_view_uses_row_copies(K):
+    """A 16-byte aligned column block of a wider matrix (lda > n): one bulk copy per row of a tile."""
+    rng = np.random.default_rng(61)
+    big = rng.standard_normal((3000, 1536))
+    view = dev(big)[:, 512:1024]
+    w, u0 = rng.standard_normal(512), rng.standard_normal(3000)
+    u = dev(u0)
+    zss = K.stream_pass(view, w=dev(w), u=u, sa=1.0, su=1.0, flags=3).cpu().numpy()
+    Aref = big[:, 512:1024]
+    u_ref = Aref @ w + u0
+    assert rel(u, u_ref) < 1e-13 and np.linalg.norm(zss[:512] - Aref.T @ u_ref) < 1e-12 * np.linalg.norm(Aref.T @ u_ref)
+
+
+def test_spo_wide_matrix_end_to_end(K):
+    """SPO on n > 8192 columns (the round-1 hard limit of the streaming pass): small m keeps it quick."""
+    import parla_b200 as rla
+    g = torch.Generator(device="cuda").manual_seed(5)
+    m, n = 12000, 8448
+    A = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    x0 = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    b = A @ x0
+    x, log = rla.SPO(rla.SkOpSJ(8), 1.2, 'qr')(A, b, 0.0, 1e-12, 60, 3)
+    assert float(torch.linalg.vector_norm(x - x0) / torch.linalg.vector_norm(x0)) < 1e-8
+
+
 def test_stream_pass_deterministic(K):
     rng = np.random.default_rng(7)
     A, w = dev(rng.standard_normal((20000, 512))), dev(rng.standard_normal(512))

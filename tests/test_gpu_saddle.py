@@ -65,8 +65,10 @@ def test_saddle_driver_matches_reference_fixture(rla, name):
         assert np.linalg.norm(y[::step] - fx["y_probe"]) <= max(tol_x, 1e-9) * float(fx["y_norm"])
     # iteration count +-1 and the logged error history
     if cond_gram * EPS < 1e-4:
+        # absolute floor: two correct PCG runs differ by O(cond(A'A + delta I) eps) |r0| in the normal-equation
+        # residual (round-off of the Gram products), so entries below that are not comparable to 1e-6
         assert_history_close(log.errors, fx["errors"], rtol=1e-6 if not lsqr_based else 1e-5,
-                             chaotic_prefix=SPS_CHAOTIC.get(name))
+                             chaotic_prefix=SPS_CHAOTIC.get(name), atol_rel=max(1e-9, 0.1 * cond_gram * EPS))
     else:       # cond(A'A) ~ 1/eps (the "tiny scale" case, cond(A) = 1e8): same convergence curve within a factor 2
         assert abs(log.errors.size - fx["errors"].size) <= 1, (log.errors.size, fx["errors"].size)
         k = min(log.errors.size, fx["errors"].size)

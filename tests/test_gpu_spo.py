@@ -100,9 +100,15 @@ def test_spo_svd_rank_deficient_matches_reference(rla, name):
         assert np.linalg.norm(x - fx["x"]) <= TOL_X * np.linalg.norm(fx["x"])
         assert np.linalg.norm(x - fx["x_minnorm"]) <= 1e-9 * np.linalg.norm(fx["x_minnorm"])   # minimum-norm solution
         assert np.linalg.norm(A @ x - b) <= 1e-12 * np.linalg.norm(b)
-        assert log.errors.size == fx["errors"].size
-        big = fx["errors"] > 1e-9 * fx["errors"][0]
-        assert np.allclose(log.errors[big], fx["errors"][big], rtol=1e-6)
+        # The presolve is accepted iff |A x_ske - b| <= 1e-15 |b| when R is non-square (least_squares.py:348): a
+        # round-off-level threshold, so an equally accurate x_ske can land on either side of it.  Same branch as the
+        # reference => same history; other branch => the presolve was accepted (one LSQR step, already converged).
+        if log.errors.size == fx["errors"].size:
+            big = fx["errors"] > 1e-9 * fx["errors"][0]
+            assert np.allclose(log.errors[big], fx["errors"][big], rtol=1e-6)
+        else:
+            assert log.errors.size == 2 and log.errors[-1] <= 1e-12 * log.errors[0]
+            assert abs(log.errors[0] - fx["errors"][0]) <= 1e-9 * fx["errors"][0]
 
 
 def test_sap1_sap2_are_spo_modes(rla):
@@ -124,13 +130,14 @@ def test_sso1_rank_deficient_sketch_is_min_norm(rla):
     dependent columns must give the pseudo-inverse solution, not inf/nan from a triangular solve."""
     rng = np.random.default_rng(6)
     A = rng.standard_normal((1500, 24))
-    A[:, 20:] = A[:, :4] @ rng.standard_normal((4, 4))                  # rank 20
+    A[:, [7, 19]] = 0.0           # rank 22 with EXACTLY zero singular values (dependent columns would leave O(eps)
+                                  # ones, which gelsd's cut-off eps * sigma_max keeps or drops by luck)
     b = rng.standard_normal(1500)
     S = orc.sjlt_operator(96, 1500, np.random.default_rng(2), 8)
     x_ref, _ = orc.SSO1(Replay(S), 4)(A, b, 0.0, np.nan, 1, None)
     x, _ = rla.SSO1(Replay(S), 4)(dev(A), dev(b), 0.0, np.nan, 1, None)
     x = x.cpu().numpy()
-    assert np.all(np.isfinite(x))
+    assert np.all(np.isfinite(x)) and abs(x[7]) <= 1e-14 and abs(x[19]) <= 1e-14
     assert np.linalg.norm(x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
 
 
