@@ -18,11 +18,13 @@ from ...parallel import allreduce_
 F64 = torch.float64
 POLL_LAG = 2      # iterations the host may run ahead of the device-side stopping test
 _POLL_CACHE = {}
-# An iteration over a small A is launch-bound (~9 launches of a few microseconds each): below this many local
-# elements of A it is captured once into a CUDA graph and replayed (the device-side stop flag already turns
-# every kernel of a replay after convergence into a no-op).  Single-GPU only: no collective inside the graph.
+# Optional (PLA_LSQR_GRAPH=1): capture one iteration into a CUDA graph and replay it (the device-side stop flag
+# already turns every kernel of a replay after convergence into a no-op; single GPU only, no collective inside).
+# OFF by default: measured on B200 at 2^16 x 500 (36 iterations) the eager loop takes 0.11 ms per iteration and
+# the replayed graph 0.22 ms -- the iteration is bound by the dependent chain of 8 short kernels, not by the host,
+# which already runs POLL_LAG iterations ahead (profiles/r2_cfg1.jsonl).
 GRAPH_MAX_ELEMS = int(os.environ.get("PLA_LSQR_GRAPH_MAX_ELEMS", 1 << 27))
-USE_GRAPH = os.environ.get("PLA_LSQR_GRAPH", "1") != "0"
+USE_GRAPH = os.environ.get("PLA_LSQR_GRAPH", "0") == "1"
 _CAPTURE_STREAMS = {}
 
 

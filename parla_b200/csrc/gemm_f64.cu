@@ -413,9 +413,10 @@ static int choose_splits(long long M, long long N, long long K) {
     const long long tiles = ((M + GM_BM - 1) / GM_BM) * ((N + GM_BN - 1) / GM_BN);
     const long long ktiles = (K + GM_BK - 1) / GM_BK;
     const long long sms = num_sms();
-    if (tiles >= 4 * sms || ktiles < 64) return 1;
-    // pick the split count whose CTA count fills whole waves best (>= 32 k-tiles per split)
-    long long smax = ktiles / 32;
+    if (tiles >= 4 * sms || ktiles < 16) return 1;
+    // pick the split count whose CTA count fills whole waves best: >= 32 k-tiles per split, or >= 8 when the output
+    // has fewer tiles than SMs (the 128 x nc products inside the QR: a handful of tiles with K = thousands of rows)
+    long long smax = ktiles / (tiles < sms ? 8 : 32);
     if (smax > 64) smax = 64;
     int best = 1;
     double best_eff = (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);

@@ -558,6 +558,7 @@ constexpr int QB_MAXG = 160;                 // >= number of SMs
 constexpr int QB_RPC_MAX = 160;              // rows per CTA (shared-memory limit)
 constexpr int QB_WLD = QR_NBO - QR_NB;       // 112: leading dimension of the W totals
 constexpr int QB_NV = QR_NB * QB_WLD + QR_NB * QR_NB;   // 2048 values per reduce-scatter
+constexpr int QB_NL = 12;                    // fan-in records per thread (>= QB_MAXG / 16, multiple of 4)
 
 struct __align__(16) LLLine { uint32_t lo, f1, hi, f2; };
 
@@ -622,7 +623,8 @@ struct BlockParams {
     int rpc;                       // rows per CTA (multiple of 16)
     LLLine* ll_step;               // [2][16][QB_MAXG] partials, ONE line per 32-byte sector (stride 2 lines)
     LLLine* ll_diag;               // [2][16] diagonal-row snapshot (owner -> everybody when G <= 16, -> reducers otherwise)
-    LLLine* ll_tot;                // [2][QB_MAXG][2][16] per-reader copies of {totals, diagonal row} (G > 16)
+    LLLine* ll_tot;                // [2][QB_MAXG][16] per-reader copies of the diagonal row (G > 16)
+    LLLine* ll_fan;                // [2][QB_MAXG readers][QB_MAXG writers][16] pushed partials (G > 16)
     LLLine* ll_bar;                // [2][QB_MAXG]
     LLLine* ll_res;                // [2][QB_NV]
     double* wpart;                 // [G][QB_NV]
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
     double* drow = red + QR_NB;                            // [16]           snapshot of the diagonal row
     double* wsum = drow + QR_NB;                           // [8][16]
     double* taus = wsum + (QB_THREADS / 32) * QR_NB;       // [16]
-    double* rsum = taus + QR_NB;                           // [9]  warp sums of a reducer + the diagonal entry
+    double* tot16 = taus + QR_NB;                          // [32] this CTA's 16 partial sums + its diagonal-row snapshot
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int G = gridDim.x, b = blockIdx.x, JB = p.JB, rpc = p.rpc;
     const long long rows = p.M - p.J0;
@@ -676,28 +678,47 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
             const uint32_t epoch = p.epoch_base + (uint32_t)gc;
             const int par = (int)(epoch & 1u);
             // The column step is written without intra-warp divergence (uniform loops closed by warp votes, PTX-
-            // predicated stores): a divergent spin / single-thread block in warp 0 cost ~7000 cycles per column
-            // on B200 (measured with clock64 around the first shared-memory read after it).
-            // (1) CTA totals of the 16 quantities, published as LL lines
+            // predicated stores): a divergent spin in warp 0 made the whole CTA wait thousands of cycles per column.
+            // Exchange = ONE hop through L2 (measured on B200: a line written by one SM is seen by a polling SM after
+            // ~2000 cycles once both dies take part; lines polled by many SMs, or reductions that need a second hop,
+            // cost 4000-8000, see scripts/ll_hop_probe.cu):
+            //   G <= 16 CTAs: each CTA publishes 16 lines, everybody polls all of them (few readers per line);
+            //   G  > 16     : each CTA PUSHES its 16 partials into a private 256-byte record of every reader
+            //                 (fan[par][reader][writer][16]: one writer and one reader per line), a reader polls its
+            //                 own G records with coalesced loads and sums them in CTA order.
+            // Every CTA adds the same numbers in the same order, so beta / tau / scale are bit-identical everywhere.
+            // (1) CTA totals of the 16 quantities
             part += __shfl_xor_sync(0xffffffffu, part, 16);
             st_shared_pred(wsum + wid * QR_NB + (lane & 15), part, lane < QR_NB);
             __syncthreads();
-            if (wid == 0) {                                  // warp-uniform
+            const bool own = gc >= l0 && gc < l0 + nloc;         // I own the diagonal row: I publish its snapshot
+            if (wid == 0) {                                      // warp-uniform
                 const int q = lane & 15;
                 const bool act = lane < QR_NB && q >= j && q < jbp;
                 double tot = 0.0;
 #pragma unroll
                 for (int w = 0; w < QB_THREADS / 32; ++w) tot += wsum[w * QR_NB + q];
-                ll_store(p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + b), tot, epoch, act);
-                const bool own = gc >= l0 && gc < l0 + nloc;     // I own the diagonal row: publish its snapshot
                 const double dv = P[(own ? (int)(gc - l0) : 0) * QB_LDP + c0 + q];
-                ll_store(p.ll_diag + par * QR_NB + q, dv, epoch, act && own);
+                if (G <= QR_NB) {
+                    ll_store(p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + b), tot, epoch, act);
+                    ll_store(p.ll_diag + par * QR_NB + q, dv, epoch, act && own);
+                } else {
+                    st_shared_pred(tot16 + q, tot, lane < QR_NB);
+                    st_shared_pred(tot16 + QR_NB + q, dv, lane < QR_NB);
+                }
+            }
+            if (G > QR_NB) {
+                __syncthreads();
+                const int q = tid & 15, r0 = tid >> 4;
+                const bool actq = q >= j && q < jbp;
+                const double tv = tot16[q], dv = tot16[QR_NB + q];
+                for (int r = r0; r < G; r += 16) {               // (CTA-uniform trip count up to the predicate)
+                    ll_store(p.ll_fan + (((size_t)(par * QB_MAXG + r)) * QB_MAXG + b) * QR_NB + q, tv, epoch, actq);
+                    ll_store(p.ll_tot + ((size_t)(par * QB_MAXG + r)) * QR_NB + q, dv, epoch, actq && own);
+                }
             }
             QB_T(1);
-            // (2) exchange.  Few CTAs (G <= 16): all-to-all, every CTA reads the G partials of each quantity (one line
-            //     per thread) and sums them in the same fixed order.  Many CTAs: all-to-all polling traffic grows as
-            //     16 G^2 lines per column and saturates the L2 slices (measured: ~5000 cycles per column at G = 86),
-            //     so quantity q is summed by ONE CTA (q mod G), which publishes the total; everybody reads 16 totals.
+            // (2) gather
             if (G <= QR_NB) {
                 const int q = tid >> 4, slot = tid & 15;
                 const bool act = q >= j && q < jbp && slot < G;
@@ -712,45 +733,56 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
                 for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                 st_shared_pred(red + q, acc, slot == 0);
             } else {
-                for (int q = j; q < jbp; ++q) {
-                    if (q % G != b) continue;                 // CTA-uniform: I am the reducer of quantity q
-                    // thread t < G polls the partial of CTA t (private sector), thread G the diagonal-row entry
-                    const bool act = tid <= G;
-                    const LLLine* line = tid < G ? p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + tid)
-                                                 : p.ll_diag + par * QR_NB + q;
-                    double val = 0.0;
-                    bool ok;
-                    do {
-                        ok = ll_try_load(line, epoch, val) || !act;
-                    } while (!__all_sync(0xffffffffu, ok));
-                    st_shared_pred(rsum + 8, val, tid == G);               // the diagonal entry is passed through
-                    if (tid >= G) val = 0.0;
-                    val = warp_sum(val);
-                    st_shared_pred(rsum + wid, val, lane == 0);
-                    __syncthreads();
+                // thread (q, bg): records of CTAs bg, bg + 16, ... ; a warp reads two consecutive 256-byte records
+                const int q = tid & 15, bg = tid >> 4;
+                const bool actq = q >= j && q < jbp;
+                const LLLine* base = p.ll_fan + (((size_t)(par * QB_MAXG + b)) * QB_MAXG + bg) * QR_NB + q;
+                double v[QB_NL];
+                unsigned pending = 0;
+#pragma unroll
+                for (int i = 0; i < QB_NL; ++i) {
+                    v[i] = 0.0;
+                    if (actq && bg + 16 * i < G) pending |= 1u << i;
+                }
+                do {
+#pragma unroll
+                    for (int g4 = 0; g4 < QB_NL / 4; ++g4) {
+                        unsigned long long w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+                        const unsigned m4 = (pending >> (4 * g4)) & 15u;
+                        ll_load4<16 * QR_NB * (int)sizeof(LLLine)>(base + (size_t)64 * QR_NB * g4, m4, w0, w1);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            double val;
+                            const bool got = ll_ready(w0[i], w1[i], epoch, val) && ((m4 >> i) & 1u);
+                            if (got) { v[4 * g4 + i] = val; pending &= ~(1u << (4 * g4 + i)); }
+                        }
+                    }
+                } while (__any_sync(0xffffffffu, pending != 0));
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < QB_NL; ++i) acc += v[i];
+                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                st_shared_pred(wsum + wid * QR_NB + q, acc, lane < QR_NB);     // (the step's wsum has been consumed)
+                __syncthreads();
+                if (wid == 1) {                                                // warp-uniform: fixed-order final sums
                     double tot = 0.0;
 #pragma unroll
-                    for (int w = 0; w < QB_THREADS / 32; ++w) tot += rsum[w];
-                    // one private copy per reader: a polled line then has exactly one writer and one reader
-                    LLLine* dst = p.ll_tot + ((size_t)(par * QB_MAXG + (tid < G ? tid : 0))) * 2 * QR_NB + q;
-                    ll_store(dst, tot, epoch, tid < G);
-                    ll_store(dst + QR_NB, rsum[8], epoch, tid < G);
-                    __syncthreads();
+                    for (int w = 0; w < QB_THREADS / 32; ++w) tot += wsum[w * QR_NB + (lane & 15)];
+                    st_shared_pred(red + (lane & 15), tot, lane < QR_NB);
                 }
             }
             if (wid == 0) {
-                // warp-uniform: lanes 0..15 fetch the totals (many-CTA scheme), lanes 16..31 the diagonal-row snapshot
+                // warp-uniform: the diagonal-row snapshot (my private copy when G > 16)
                 const int qd = lane & 15;
-                const bool is_tot = lane < QR_NB;
-                const bool need = qd >= j && qd < jbp && (!is_tot || G > QR_NB);
-                const LLLine* line = G > QR_NB ? p.ll_tot + ((size_t)(par * QB_MAXG + b)) * 2 * QR_NB + lane
+                const bool need = lane < QR_NB && qd >= j && qd < jbp;
+                const LLLine* line = G > QR_NB ? p.ll_tot + ((size_t)(par * QB_MAXG + b)) * QR_NB + qd
                                                : p.ll_diag + par * QR_NB + qd;
                 double dv = 0.0;
                 bool ok;
                 do {
                     ok = ll_try_load(line, epoch, dv) || !need;
                 } while (!__all_sync(0xffffffffu, ok));
-                st_shared_pred((is_tot ? red : drow) + qd, dv, need);
+                st_shared_pred(drow + qd, dv, need);
             }
             __syncthreads();
             QB_T(2);
@@ -784,28 +816,19 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
                 __syncwarp();                               // every lane has read the old rows before anyone writes
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    // branch-free (selects + predicated store): lanes c < j, c == j, c > j and the diagonal row would
+                    // otherwise serialise as separate divergent paths
                     const int r = g + QR_NB * (it0 + u);
                     const bool valid = it0 + u < nit && r < nloc;
                     const long long li = l0 + r;
-                    double* row = P + (valid ? r : 0) * QB_LDP + c0;
-                    if (valid && li >= gc) {
-                        if (li == gc) {
-                            if (c == j) row[c] = beta;
-                            else if (c > j && c < jbp) row[c] = ac[u] - wv_c;
-                        } else {
-                            const double v = aj[u] * scale;
-                            if (c == j) {
-                                row[c] = v;
-                            } else if (c > j && c < jbp) {
-                                const double anew = fma(-v, wv_c, ac[u]);
-                                row[c] = anew;
-                                if (li > gc + 1) {
-                                    const double x = (c == j + 1) ? anew : fma(-v, wv_n, an[u]);
-                                    part = fma(x, anew, part);
-                                }
-                            }
-                        }
-                    }
+                    const bool diag = li == gc;
+                    const double vv = diag ? 1.0 : aj[u] * scale;              // reflector entry of this row
+                    const double anew = fma(-vv, wv_c, ac[u]);                 // (wv_c = 0 for c <= j)
+                    const double out = (c == j) ? (diag ? beta : vv) : anew;
+                    if (valid && li >= gc && c >= j && c < jbp) P[r * QB_LDP + c0 + c] = out;
+                    const double x = (c == j + 1) ? anew : fma(-vv, wv_n, an[u]);
+                    const bool cnt = valid && li > gc + 1 && c > j && c < jbp;
+                    part = fma(cnt ? x : 0.0, anew, part);
                 }
             }
             QB_T(11);
@@ -1102,7 +1125,8 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
     const size_t o_w2s = take((size_t)QR_NB * (size_t)(N > 0 ? N : 1) * 8);
     const size_t o_vx = take((size_t)M * QR_NBO * 8);
     const size_t o_gb = take((size_t)QR_NBO * QR_NBO * 8);
-    const size_t ll_lines = (size_t)4 * QR_NB * QB_MAXG + 2 * QR_NB + (size_t)4 * QB_MAXG * QR_NB + 2 * QB_MAXG + 2 * QB_NV;
+    const size_t ll_lines = (size_t)4 * QR_NB * QB_MAXG + 2 * QR_NB + (size_t)2 * QB_MAXG * QR_NB + 2 * QB_MAXG + 2 * QB_NV +
+                            (size_t)2 * QB_MAXG * QB_MAXG * QR_NB;
     const size_t o_ll = take(ll_lines * sizeof(LLLine));
     const size_t o_cp = take((size_t)QB_MAXG * QB_NV * 8);
     const size_t o_pf = take((size_t)QB_MAXG * QB_NPROF * 8);
@@ -1236,14 +1260,15 @@ static int run_block_coop(double* A, long long lda, long long M, long long J0, i
     bp.ll_step = w.ll;
     bp.ll_diag = bp.ll_step + (size_t)4 * QR_NB * QB_MAXG;
     bp.ll_tot = bp.ll_diag + 2 * QR_NB;
-    bp.ll_bar = bp.ll_tot + (size_t)4 * QB_MAXG * QR_NB;
+    bp.ll_bar = bp.ll_tot + (size_t)2 * QB_MAXG * QR_NB;
     bp.ll_res = bp.ll_bar + 2 * QB_MAXG;
+    bp.ll_fan = bp.ll_res + 2 * QB_NV;
     bp.wpart = w.cpart;
     bp.epoch_base = epoch_base;
     static const bool prof = [] { const char* e = getenv("PLA_QR_PROF"); return e && e[0] == '1'; }();
     bp.prof = prof ? w.prof : nullptr;
     const size_t smem = ((size_t)rpc * QB_LDP + (size_t)rpc * QR_NB + QR_NB * QB_WLD + QR_NB * QR_NB + 3 * QR_NB +
-                         (QB_THREADS / 32) * QR_NB + QB_THREADS / 32 + 2) * sizeof(double);
+                         (QB_THREADS / 32) * QR_NB + 2 * QR_NB) * sizeof(double);
     PLA_CUDA(cudaFuncSetAttribute(qr_block_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&bp};
     PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_block_coop_kernel, dim3((unsigned)G), dim3(QB_THREADS), args,

@@ -268,23 +268,41 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
     }
 }
 
-// zss[c] = sum_b zpart[b][c] (fixed order), zss[n] = sum_b sspart[b]
-__global__ void __launch_bounds__(256) stream_pass_reduce_kernel(const double* __restrict__ zpart,
-                                                                 const double* __restrict__ sspart, int nblk,
-                                                                 long long n, double* __restrict__ zss, int do_axpy,
-                                                                 const int* istop) {
+// zss[c] = sum_b zpart[b][c], zss[n] = sum_b sspart[b], both in a fixed order (bit-reproducible).
+// A CTA owns 32 columns; its 8 warps each sum every 8th partial (8 independent loads in flight per thread), the 8
+// warp results are added in warp order.  (One thread per column walking all ~600 partials serially cost 30-40 us,
+// several times the streaming pass itself on a 2^16 x 500 matrix.)
+constexpr int SPR_COLS = 32, SPR_WARPS = 8;
+__global__ void __launch_bounds__(SPR_COLS * SPR_WARPS) stream_pass_reduce_kernel(const double* __restrict__ zpart,
+                                                                                   const double* __restrict__ sspart,
+                                                                                   int nblk, long long n,
+                                                                                   double* __restrict__ zss, int do_axpy,
+                                                                                   const int* istop) {
     if (istop != nullptr && *istop != 0) return;
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) {
-        double acc = 0.0;
-        if (do_axpy)
-            for (int b = 0; b < nblk; ++b) acc += zpart[(size_t)b * n + c];
-        zss[c] = acc;
+    __shared__ double acc_s[SPR_WARPS][SPR_COLS + 1];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * SPR_COLS + cl;      // column n is the |u|^2 slot
+    double acc = 0.0;
+    if (c < n ? do_axpy != 0 : c == n) {
+        const double* src = c < n ? zpart + c : sspart;
+        const long long stride = c < n ? n : 1;
+        for (int b0 = grp; b0 < nblk; b0 += SPR_WARPS * 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = b0 + SPR_WARPS * u;
+                t[u] = b < nblk ? src[(size_t)b * stride] : 0.0;
+            }
+            acc += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+        }
     }
-    if (c == n) {
-        double acc = 0.0;
-        for (int b = 0; b < nblk; ++b) acc += sspart[b];
-        zss[n] = acc;
+    acc_s[grp][cl] = acc;
+    __syncthreads();
+    if (grp == 0 && c <= n) {
+        double tot = 0.0;
+#pragma unroll
+        for (int g2 = 0; g2 < SPR_WARPS; ++g2) tot += acc_s[g2][cl];
+        zss[c] = tot;
     }
 }
 
@@ -389,8 +407,9 @@ extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_
     }
 #undef PLA_SP_CASE
     if (e != cudaSuccess) { set_error("pla_stream_pass_f64: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
-    const int rb = (int)((n + 1 + 255) / 256);
-    stream_pass_reduce_kernel<<<rb, 256, 0, st>>>(p.zpart, p.sspart, nparts, n, zss, do_axpy ? 1 : 0, istop_dev);
+    const int rb = (int)((n + 1 + SPR_COLS - 1) / SPR_COLS);
+    stream_pass_reduce_kernel<<<rb, SPR_COLS * SPR_WARPS, 0, st>>>(p.zpart, p.sspart, nparts, n, zss, do_axpy ? 1 : 0,
+                                                                  istop_dev);
     PLA_LAUNCH_CHECK();
     return 0;
 }
