@@ -377,6 +377,8 @@ def strong_record(rla, K, a, rank, world, dev, barrier, dist):
 
 
 def run_gpu_arm(a):
+    # a freed 64 GiB block must really go back to the driver before the 128 GiB strong-scaling shard is allocated
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -540,6 +542,9 @@ def run_gpu_arm(a):
         del Ah, bh, Ahs, bhs
     else:
         del A, b, Ash, bsh
+    alg.last_residual = None
+    x = log = None
+    K.Workspace._bufs.clear()
     torch.cuda.empty_cache()
 
     if not a.no_extras:

@@ -60,21 +60,32 @@ def dim_checks(sampling_factor, n_rows, n_cols):
     return d
 
 
-def _to_device(A, b):
-    """Accept HOST buffers (numpy arrays or CPU torch tensors, ideally pinned): upload them on the
-    current stream and remember to hand the result back on the host.  -> (A, b, host_kind)"""
+def _to_device(A, b, defer=False):
+    """Accept HOST buffers (numpy arrays, CPU torch tensors or RowSharded shards of those; ideally pinned).
+    -> (A, b, host_kind).  With ``defer`` the upload is left to :func:`_sketch`, which streams it in row blocks on a
+    copy stream while the blocks already on the device are being sketched."""
     host = None
-    if isinstance(A, np.ndarray):
+    A_loc, b_loc = unwrap(A)[0], (None if b is None else unwrap(b)[0])
+    if isinstance(A_loc, np.ndarray):
         host = "numpy"
-        A = torch.from_numpy(np.ascontiguousarray(A, dtype=np.float64))
-        b = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64))
-    elif isinstance(A, torch.Tensor) and not A.is_cuda:
+        A_loc = torch.from_numpy(np.ascontiguousarray(A_loc, dtype=np.float64))
+        b_loc = None if b_loc is None else torch.from_numpy(np.ascontiguousarray(b_loc, dtype=np.float64))
+    elif isinstance(A_loc, torch.Tensor) and not A_loc.is_cuda:
         host = "torch"
-    if host is not None:
+    if host is None:
+        return A, b, None
+    if not defer:
         dev = torch.device("cuda", torch.cuda.current_device())
-        A = A.to(dev, non_blocking=True)
-        b = b.to(dev, non_blocking=True)
-    return A, b, host
+        A_loc = A_loc.to(dev, non_blocking=True)
+        b_loc = None if b_loc is None else b_loc.to(dev, non_blocking=True)
+    return _like_input(A, A_loc), (None if b is None else _like_input(b, b_loc)), host
+
+
+def _like_input(orig, local):
+    """Re-wrap a local block the way ``orig`` was given (RowSharded or plain)."""
+    if isinstance(orig, RowSharded):
+        return RowSharded(local, orig.row_offset, orig.m_global, orig.group)
+    return local
 
 
 def _to_host(x, host):
@@ -85,22 +96,77 @@ def _to_host(x, host):
     return x
 
 
-def _sketch(sketch_op_gen, d, A, b, delta, rng):
-    """[A_ske | b_ske] (+ ridge rows) in one (d [+ n]) x (n + 1) row-major buffer."""
+UPLOAD_BLOCKS = int(os.environ.get("PLA_UPLOAD_BLOCKS", "8"))
+_COPY_STREAMS = {}
+
+
+def _streamed_sketch(S, A_host, b_host, W, row_off, stats):
+    """Upload a host-resident block of rows in ``UPLOAD_BLOCKS`` pieces on a copy stream and sketch every piece as
+    soon as it has arrived (``W += S[:, piece] [A | b][piece]``): the sketch costs no time on top of the PCIe
+    transfer.  Returns the device copies (A, b); ``stats`` receives bytes and the copy stream's seconds."""
+    dev = W.device
+    m_loc, n = A_host.shape
+    main = torch.cuda.current_stream()
+    key = torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream()
+    cs = _COPY_STREAMS[key]
+    A_dev = torch.empty(m_loc, n, dtype=F64, device=dev)
+    b_dev = None if b_host is None else torch.empty(m_loc, dtype=F64, device=dev)
+    step = max(4096, -(-m_loc // max(1, UPLOAD_BLOCKS)) // 4096 * 4096)       # multiple of 4096 rows
+    bounds = [(r0, min(r0 + step, m_loc)) for r0 in range(0, m_loc, step)]
+    cs.wait_stream(main)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    arrived = []
+    with torch.cuda.stream(cs):
+        t0.record()
+        for r0, r1 in bounds:
+            A_dev[r0:r1].copy_(A_host[r0:r1], non_blocking=True)
+            if b_dev is not None:
+                b_dev[r0:r1].copy_(b_host[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            arrived.append(ev)
+        t1.record()
+    for i, (r0, r1) in enumerate(bounds):
+        main.wait_event(arrived[i])
+        piece = S.column_slice(r0, r1 - r0)
+        piece.sketch_into(A_dev[r0:r1], None if b_dev is None else b_dev[r0:r1], W, row_offset=row_off + r0,
+                          accumulate=i > 0)
+    stats["bytes"] = m_loc * n * 8 + (0 if b_host is None else m_loc * 8)
+    stats["events"] = (t0, t1)
+    return A_dev, b_dev
+
+
+def _sketch(sketch_op_gen, d, A, b, delta, rng, upload=None):
+    """[A_ske | b_ske] (+ ridge rows) in one (d [+ n]) x (n + 1) row-major buffer.  With ``upload`` (a dict) a
+    host-resident A / b is uploaded here, overlapped with the sketch; the device copies are returned in it."""
     A_loc, row_off, group = unwrap(A)
-    b_loc = unwrap(b)[0]
+    b_loc = None if b is None else unwrap(b)[0]
     m, n = A.shape
+    on_host = not A_loc.is_cuda
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_host else A_loc.device
     with shard_context(row_off, A_loc.shape[0]):
-        S = as_device_operator(sketch_op_gen(d, m, rng), A_loc.device)
+        S = as_device_operator(sketch_op_gen(d, m, rng), dev)
     if S.shape[1] != A_loc.shape[0]:           # a full-width operator (e.g. a replayed reference S)
         S = S.column_slice(row_off, A_loc.shape[0])
     d_aug = d + (n if delta > 0 else 0)
     # even leading dimension (16-byte aligned rows) so the QR's tensor-core trailing updates and
     # the sketch kernels can use vector accesses; the pad column is kept at zero
     ld = n + 1 + ((n + 1) % 2)
-    Wfull = torch.zeros(d_aug, ld, dtype=F64, device=A_loc.device)
+    Wfull = torch.zeros(d_aug, ld, dtype=F64, device=dev)
     W = Wfull[:, :n + 1]
-    S.sketch_into(A_loc, b_loc, W[:d], row_offset=row_off)
+    if on_host:
+        from ..utils.sketching import GaussianOperator, SJLTOperator
+        if isinstance(S, (GaussianOperator, SJLTOperator)) and A_loc.shape[0] >= 2 * 4096:
+            A_dev, b_dev = _streamed_sketch(S, A_loc, b_loc, W[:d], row_off, upload)
+        else:                                   # other operators need the whole block: plain upload, then sketch
+            A_dev = A_loc.to(dev, non_blocking=True)
+            b_dev = None if b_loc is None else b_loc.to(dev, non_blocking=True)
+            S.sketch_into(A_dev, b_dev, W[:d], row_offset=row_off)
+        upload["A"], upload["b"] = _like_input(A, A_dev), (None if b is None else _like_input(b, b_dev))
+    else:
+        S.sketch_into(A_loc, b_loc, W[:d], row_offset=row_off)
     allreduce_(Wfull[:d], group)
     if delta > 0:
         W[d:, :].zero_()
@@ -194,22 +260,27 @@ class SPO(OverLstsqSolver):
         self.iterative_solver = dsad.PcSS2()  # implements LSQR
 
     def __call__(self, A, b, delta, tol, iter_lim, rng, logging=True):
-        A, b, host = _to_device(A, b)
+        A, b, host = _to_device(A, b, defer=True)
         n_rows, n_cols = A.shape
         sqrt_delta = math.sqrt(delta)
         d = dim_checks(self.sampling_factor, n_rows, n_cols)
         rng = np.random.default_rng(rng)
-        A_loc, _, group = unwrap(A)
-        b_loc = unwrap(b)[0]
-        dev = A_loc.device
 
         quick_time = _clock(logging)
         log = SketchAndPrecondLog()
 
         # Sketch the data matrix (and the right-hand side, same kernel)            :302-303, :314
+        # (host-resident A / b: uploaded here in row blocks, each block sketched while the next one is in flight)
         tic = quick_time()
-        S, W = _sketch(self.sketch_op_gen, d, A, b, delta, rng)
+        upload = {} if host is not None else None
+        S, W = _sketch(self.sketch_op_gen, d, A, b, delta, rng, upload=upload)
+        if host is not None:
+            A, b = upload.pop("A"), upload.pop("b")
+            self._upload_stats = upload          # (bytes + the copy stream's events only: no reference to A)
         log.time_sketch = quick_time() - tic
+        A_loc, _, group = unwrap(A)
+        b_loc = unwrap(b)[0]
+        dev = A_loc.device
 
         # Factor the sketch; sketch-and-solve presolve                              :306-341
         n = n_cols
@@ -296,6 +367,16 @@ class SPO(OverLstsqSolver):
         return _to_host(x, host), log
 
     exec = __call__
+
+    @property
+    def last_upload(self):
+        """{'bytes', 'seconds'} of the last host -> device upload done inside a call (None for device inputs)."""
+        st = getattr(self, "_upload_stats", None)
+        if not st or "events" not in st:
+            return None
+        t0, t1 = st["events"]
+        t1.synchronize()
+        return {"bytes": st["bytes"], "seconds": t0.elapsed_time(t1) * 1e-3}
 
 
 class SAP1(SPO):

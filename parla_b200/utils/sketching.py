@@ -93,10 +93,11 @@ class GaussianOperator(SketchOperator):
         self.seed, self.scale = int(seed), float(scale)
         self.device = _device(device)
 
-    def sketch_into(self, A, b, out, row_offset=0):
+    def sketch_into(self, A, b, out, row_offset=0, accumulate=False):
         if row_offset % 4:
             raise ValueError("row shards must start at a multiple of 4 rows")
-        K.sketch_gauss(A, self.shape[0], self.seed, self.scale, out, bvec=b, col_offset=row_offset)
+        K.sketch_gauss(A, self.shape[0], self.seed, self.scale, out, bvec=b, col_offset=row_offset,
+                       beta=1.0 if accumulate else 0.0)
         return out
 
     def apply(self, A):
@@ -124,11 +125,19 @@ class SJLTOperator(SketchOperator):
         self.shape = (int(n_rows), rows.shape[0])
         self.vec_nnz = rows.shape[1]
         self.scale = 1.0 / math.sqrt(self.vec_nnz)
-        self.plan = K.SjltPlan(rows, signs, n_rows, validate=validate)
+        self._plan = K.SjltPlan(rows, signs, n_rows, validate=True) if validate else None
 
-    def sketch_into(self, A, b, out, row_offset=0):
+    @property
+    def plan(self):
+        """Destination-major plan, built on first use (an operator that is only sliced into row blocks, or only
+        used through its adjoint, never needs the plan over all its columns)."""
+        if self._plan is None:
+            self._plan = K.SjltPlan(self.rows, self.signs, self.shape[0])
+        return self._plan
+
+    def sketch_into(self, A, b, out, row_offset=0, accumulate=False):
         n = A.shape[1]
-        self.plan.apply(A, self.scale, out, bvec=b, out_b=None if b is None else out[:, n])
+        self.plan.apply(A, self.scale, out, bvec=b, out_b=None if b is None else out[:, n], accumulate=accumulate)
         return out
 
     def apply(self, A):

@@ -165,6 +165,30 @@ def test_spo_host_buffers_in_numpy_out(rla):
     assert np.linalg.norm(x - x_opt) <= 1e-9 * np.linalg.norm(x_opt)
 
 
+@pytest.mark.parametrize("gen_name", ["SkOpSJ", "SkOpGA"])
+def test_spo_streamed_upload_of_pinned_host_buffers(rla, gen_name):
+    """Host-resident (pinned) A, b: uploaded in row blocks on a copy stream, each block sketched as it arrives
+    (the e2e path of bench.py).  Same x as with device-resident inputs, to the stated tolerance."""
+    rng = np.random.default_rng(31)
+    m, n = 70000, 96
+    A = rng.standard_normal((m, n)) * np.logspace(0, 2, n)
+    b = A @ rng.standard_normal(n) + 0.1 * rng.standard_normal(m)
+    gen = getattr(rla, gen_name)
+    gen = gen(8) if gen_name == "SkOpSJ" else gen()
+    Ah, bh = torch.from_numpy(A).pin_memory(), torch.from_numpy(b).pin_memory()
+    alg = rla.SPO(gen, 4, 'qr')
+    xh, _ = alg(Ah, bh, 0.0, 1e-12, 100, 9)
+    assert isinstance(xh, torch.Tensor) and not xh.is_cuda
+    up = alg.last_upload
+    assert up is not None and up["bytes"] == m * n * 8 + m * 8 and up["seconds"] > 0
+    xd, _ = rla.SPO(gen, 4, 'qr')(dev(A), dev(b), 0.0, 1e-12, 100, 9)
+    assert np.linalg.norm(xh.numpy() - xd.cpu().numpy()) <= TOL_X * np.linalg.norm(xd.cpu().numpy())
+    x_opt = np.linalg.lstsq(A, b, rcond=None)[0]
+    assert np.linalg.norm(xh.numpy() - x_opt) <= 1e-9 * np.linalg.norm(x_opt)
+    xn, _ = alg(A, b, 0.0, 1e-12, 100, 9)                      # pageable numpy buffers take the same path
+    assert isinstance(xn, np.ndarray) and np.linalg.norm(xn - xh.numpy()) <= TOL_X * np.linalg.norm(xn)
+
+
 @pytest.mark.parametrize("gen_name", ["SkOpSJ", "SkOpGA", "sjlt_operator", "gaussian_operator"])
 @pytest.mark.parametrize("mode", ["qr", "svd"])
 def test_native_operators_convergence_rate(rla, gen_name, mode):
