@@ -248,6 +248,18 @@ int pla_philox_normal_fill_f64(double* out, int64_t rows, int64_t cols, int64_t 
 size_t pla_qr_workspace_bytes(int64_t M, int64_t N);
 int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64_t ncols_factor, double* tau, void* ws,
                   size_t ws_bytes, void* stream);
+/* Block-level pieces of pla_geqrf_f64 for a QR whose trailing columns are spread over several GPUs (the replicated
+ * d x (n+1) sketch of the row-sharded solvers, least_squares.py:311): every rank factors the same 128-column panel,
+ * each rank updates only the columns it owns.
+ *   factor: Householder QR of A[r0:M, c0:c0+jb] in place (jb <= 128; LAPACK conventions), tau_blk[0:jb]; leaves the
+ *           explicit reflector block and its Gram matrix in `ws`.  block_index = 0 resets the workspace's exchange lines;
+ *           it must increase by one per call within one factorisation.
+ *   apply : C[r0:M, 0:nc] <- H_jb ... H_1 C with the reflectors left in `ws` by the last factor call.
+ * Both calls must pass the same M, `n_layout` (>= 128 and >= every nc) and workspace (pla_qr_workspace_bytes(M, n_layout)). */
+int pla_qr_factor_block_f64(double* A, int64_t M, int64_t lda, int64_t r0, int64_t c0, int64_t jb, double* tau_blk,
+                            int block_index, int64_t n_layout, void* ws, size_t ws_bytes, void* stream);
+int pla_qr_apply_block_f64(int64_t M, int64_t r0, int64_t jb, const double* tau_blk, double* C, int64_t ldc, int64_t nc,
+                           int64_t n_layout, void* ws, size_t ws_bytes, void* stream);
 int pla_orgqr_f64(const double* A, int64_t M, int64_t K, int64_t lda, const double* tau, double* Q, int64_t ldq,
                   void* ws, size_t ws_bytes, void* stream);
 

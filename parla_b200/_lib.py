@@ -58,6 +58,8 @@ SIGNATURES = {
     "pla_philox_normal_fill_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_u64, c_i64, c_i64, c_dbl, c_vp]),
     "pla_qr_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "pla_geqrf_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "pla_qr_factor_block_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_sz, c_vp]),
+    "pla_qr_apply_block_f64": (c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_sz, c_vp]),
     "pla_orgqr_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "pla_sumsq_workspace_bytes": (c_sz, [c_i64]),
     "pla_sumsq_f64": (c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

@@ -617,8 +617,9 @@ __device__ __forceinline__ void st_global_pred(double* p, double v, bool pred) {
 
 struct BlockParams {
     double* A; long long lda; long long M;
-    long long J0; int JB;          // block = columns [J0, J0 + JB), rows [J0, M)
-    double* tau;                   // tau + J0
+    long long J0; int JB;          // block = columns [C0, C0 + JB), rows [J0, M)  (C0 == J0 inside pla_geqrf_f64)
+    long long C0;
+    double* tau;                   // the block's JB scalar factors
     double* Vx;                    // out: (M - J0) x 128 explicit reflectors (unit diagonal, zeros above / right of JB)
     int rpc;                       // rows per CTA (multiple of 16)
     LLLine* ll_step;               // [2][16][QB_MAXG] partials, ONE line per 32-byte sector (stride 2 lines)
@@ -652,7 +653,7 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
     const long long l0 = (long long)b * rpc;               // block-local index of my first row
     const int nloc = (int)max(0LL, min((long long)rpc, rows - l0));
     const int nit = rpc / QR_NB;                           // row sweeps of the 16 x 16 thread grid
-    double* Ablk = p.A + p.J0 * p.lda + p.J0;
+    double* Ablk = p.A + p.J0 * p.lda + p.C0;
     long long pacc[QB_NPROF], plast = clock64();
 #pragma unroll
     for (int i = 0; i < QB_NPROF; ++i) pacc[i] = 0;
@@ -1243,8 +1244,8 @@ using namespace pla;
 extern "C" size_t pla_qr_workspace_bytes(int64_t M, int64_t N) { return qr_ws_layout(M, N, nullptr, nullptr); }
 
 // Cooperative factorisation of the block (J0, JB); returns 1 when the block does not fit (caller falls back).
-static int run_block_coop(double* A, long long lda, long long M, long long J0, int JB, double* tau, const QrWs& w,
-                          uint32_t epoch_base, cudaStream_t st) {
+static int run_block_coop(double* A, long long lda, long long M, long long J0, long long C0, int JB, double* tau_blk,
+                          const QrWs& w, uint32_t epoch_base, cudaStream_t st) {
     static const int target = [] { const char* e = getenv("PLA_QR_RPC"); int v = e ? atoi(e) : 96; return v < 16 ? 96 : v; }();
     const long long rows = M - J0;
     const int sms = num_sms() < QB_MAXG ? num_sms() : QB_MAXG;
@@ -1256,7 +1257,7 @@ static int run_block_coop(double* A, long long lda, long long M, long long J0, i
     if (rpc > QB_RPC_MAX) return 1;
     G = (rows + rpc - 1) / rpc;
     BlockParams bp;
-    bp.A = A; bp.lda = lda; bp.M = M; bp.J0 = J0; bp.JB = JB; bp.tau = tau + J0; bp.Vx = w.Vx; bp.rpc = (int)rpc;
+    bp.A = A; bp.lda = lda; bp.M = M; bp.J0 = J0; bp.C0 = C0; bp.JB = JB; bp.tau = tau_blk; bp.Vx = w.Vx; bp.rpc = (int)rpc;
     bp.ll_step = w.ll;
     bp.ll_diag = bp.ll_step + (size_t)4 * QR_NB * QB_MAXG;
     bp.ll_tot = bp.ll_diag + 2 * QR_NB;
@@ -1306,7 +1307,7 @@ static int build_block_reflector(const double* A, long long lda, long long M, lo
 }
 
 // C[J0:M, 0:nc] <- (I - Vx op(T) Vx^T) C: two DMMA GEMMs around the substitution kernel (T never formed)
-static int apply_block_reflector(long long M, long long J0, int JB, const double* tau, double* C, long long ldc,
+static int apply_block_reflector(long long M, long long J0, int JB, const double* tau_blk, double* C, long long ldc,
                                  long long nc, int t_transpose, const QrWs& w, cudaStream_t st) {
     if (nc <= 0) return 0;
     const long long rows = M - J0;
@@ -1317,7 +1318,7 @@ static int apply_block_reflector(long long M, long long J0, int JB, const double
     const size_t smem = ((size_t)QR_NBO * QR_NBO + (size_t)QR_NBO * QW_THREADS + QR_NBO) * sizeof(double);
     PLA_CUDA(cudaFuncSetAttribute(qr_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     qr_w2_kernel<<<(unsigned)((nc + QW_THREADS - 1) / QW_THREADS), QW_THREADS, smem, st>>>(
-        w.Gbig, tau + J0, JB, w.Wbig, nc, nc, w.W2big, nc, t_transpose);          // W2 = op(T) W
+        w.Gbig, tau_blk, JB, w.Wbig, nc, nc, w.W2big, nc, t_transpose);           // W2 = op(T) W
     PLA_LAUNCH_CHECK();
     return pla_gemm_f64(0, 0, rows, nc, QR_NBO, -1.0, w.Vx, QR_NBO, w.W2big, nc, 1.0, Crows, ldc, w.gemm_ws,
                         w.gemm_ws_bytes, st);                                     // C -= Vx W2
@@ -1346,7 +1347,7 @@ extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64
                 PLA_CUDA(cudaMemsetAsync(w.ll, 0, w.ll_bytes, st));
                 ll_clean = true;
             }
-            const int rc = run_block_coop(A, lda, M, J0, JB, tau, w, (blk + 1u) * 256u, st);
+            const int rc = run_block_coop(A, lda, M, J0, J0, JB, tau + J0, w, (blk + 1u) * 256u, st);
             if (rc < 0 || rc > 1) return rc;
             done = (rc == 0);
         }
@@ -1364,11 +1365,43 @@ extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64
         if (nc > 0) {
             int rc = build_block_reflector(A, lda, M, J0, JB, done, w, st);
             if (rc) return rc;
-            rc = apply_block_reflector(M, J0, JB, tau, A + J0 + JB, lda, nc, /*T^T*/ 1, w, st);
+            rc = apply_block_reflector(M, J0, JB, tau + J0, A + J0 + JB, lda, nc, /*T^T*/ 1, w, st);
             if (rc) return rc;
         }
     }
     return 0;
+}
+
+// ---- block-level entry points: a QR whose trailing columns are spread over several GPUs (distla.geqrf_distributed)
+extern "C" int pla_qr_factor_block_f64(double* A, int64_t M, int64_t lda, int64_t r0, int64_t c0, int64_t jb, double* tau_blk,
+                                       int block_index, int64_t n_layout, void* ws, size_t ws_bytes, void* stream) {
+    PLA_CHECK_ARG(A != nullptr, 1, "A is null");
+    PLA_CHECK_ARG(M >= 1 && r0 >= 0 && r0 < M, 4, "row offset out of range");
+    PLA_CHECK_ARG(c0 >= 0 && jb >= 1 && jb <= QR_NBO && lda >= c0 + jb, 6, "bad block columns (jb <= 128, c0 + jb <= lda)");
+    PLA_CHECK_ARG(M - r0 >= jb, 6, "block has fewer rows than columns");
+    PLA_CHECK_ARG(tau_blk != nullptr && block_index >= 0, 7, "bad tau / block index");
+    PLA_CHECK_ARG(n_layout >= QR_NBO && ws != nullptr && ws_bytes >= pla_qr_workspace_bytes(M, n_layout), 10,
+                  "n_layout < 128 or workspace too small");
+    QrWs w;
+    qr_ws_layout(M, n_layout, ws, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (block_index == 0) PLA_CUDA(cudaMemsetAsync(w.ll, 0, w.ll_bytes, st));
+    int rc = run_block_coop(A, lda, M, r0, c0, (int)jb, tau_blk, w, ((uint32_t)block_index + 1u) * 256u, st);
+    if (rc == 1) { set_error("pla_qr_factor_block_f64: %lld rows do not fit the cooperative block kernel", (long long)(M - r0)); return -2; }
+    if (rc) return rc;
+    return build_block_reflector(A, lda, M, r0, (int)jb, true, w, st);
+}
+
+extern "C" int pla_qr_apply_block_f64(int64_t M, int64_t r0, int64_t jb, const double* tau_blk, double* C, int64_t ldc,
+                                      int64_t nc, int64_t n_layout, void* ws, size_t ws_bytes, void* stream) {
+    PLA_CHECK_ARG(M >= 1 && r0 >= 0 && r0 < M && jb >= 1 && jb <= QR_NBO, 2, "bad block");
+    PLA_CHECK_ARG(tau_blk != nullptr, 4, "tau is null");
+    PLA_CHECK_ARG(nc == 0 || (C != nullptr && ldc >= nc), 5, "bad C / ldc");
+    PLA_CHECK_ARG(n_layout >= QR_NBO && n_layout >= nc && ws != nullptr && ws_bytes >= pla_qr_workspace_bytes(M, n_layout), 8,
+                  "n_layout too small or workspace too small");
+    QrWs w;
+    qr_ws_layout(M, n_layout, ws, &w);           // same layout as the factor call that left Vx and the Gram matrix here
+    return apply_block_reflector(M, r0, (int)jb, tau_blk, C, ldc, nc, /*T^T*/ 1, w, (cudaStream_t)stream);
 }
 
 extern "C" int pla_orgqr_f64(const double* A, int64_t M, int64_t K, int64_t lda, const double* tau, double* Q,
@@ -1391,7 +1424,7 @@ extern "C" int pla_orgqr_f64(const double* A, int64_t M, int64_t K, int64_t lda,
         const int JB = (int)((K - J0) < QR_NBO ? (K - J0) : QR_NBO);
         int rc = build_block_reflector(A, lda, M, J0, JB, false, w, st);
         if (rc) return rc;
-        rc = apply_block_reflector(M, J0, JB, tau, Q + J0, ldq, K - J0, /*T*/ 0, w, st);
+        rc = apply_block_reflector(M, J0, JB, tau + J0, Q + J0, ldq, K - J0, /*T*/ 0, w, st);
         if (rc) return rc;
     }
     return 0;

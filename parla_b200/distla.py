@@ -105,3 +105,80 @@ def local(X):
 
 def clone(X):
     return _like(X.local.clone(), X) if isinstance(X, RowSharded) else X.clone()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# QR of the REPLICATED d x (n + 1) sketch [A_ske | b_ske] with the trailing columns spread over the ranks.
+QR_DIST_MIN_BLOCKS_PER_RANK = 2
+QR_DIST_MAX_ROWS = 148 * 160        # capacity of the cooperative block kernel (csrc/qr.cu: QB_RPC_MAX rows per SM)
+
+
+def geqrf_distributed_ok(d, n, group):
+    """Worth it (and possible) when every rank gets at least two 128-column blocks and a panel fits the
+    cooperative kernel; otherwise callers use the replicated K.geqrf."""
+    if group is None or not dist.is_initialized():
+        return False
+    world = dist.get_world_size(group)
+    return world > 1 and d <= QR_DIST_MAX_ROWS and n >= QR_DIST_MIN_BLOCKS_PER_RANK * K.QR_BLOCK * world
+
+
+def geqrf_distributed(W, n, group):
+    """In-place Householder QR of the first n columns of W (d x (n + 1), identical on every rank; the last column is
+    carried along as a right-hand side), replacing ``la.qr(A_ske)`` + ``Q.T @ b_ske`` (least_squares.py:311,315)
+    when A is row-sharded.  After the sketch all-reduce every rank would otherwise repeat the whole factorisation --
+    the Amdahl term of strong scaling (44 % of an 8-GPU solve at 16384 x 4097 in round 1).  Here:
+
+      * 128-column blocks are dealt to the ranks round-robin; a rank keeps its blocks PACKED (d x n/P, contiguous)
+        plus its own copy of the right-hand-side column;
+      * per block: the owner broadcasts the current panel (d x 128, NCCL over NVLink), EVERY rank factors it with the
+        cooperative block kernel (identical bits everywhere: same input, deterministic kernel) and applies the block
+        reflector to its own packed trailing columns only -- the tensor-core trailing updates, ~70 % of the
+        factorisation, are divided by the number of ranks;
+      * the R factor (rows 0..n-1 of the packed blocks) is all-gathered at the end.
+
+    On return ``triu(W[:n, :n]) = R`` and ``W[:n, n] = (Q^T [b_ske; 0])[:n]`` on every rank, as after K.geqrf (the
+    reflectors below the diagonal are NOT gathered: the solvers never form Q)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    d = W.shape[0]
+    nb = K.QR_BLOCK
+    nblk = (n + nb - 1) // nb
+    mine = list(range(rank, nblk, world))                      # global indices of my blocks
+    widths = [min(nb, n - nb * j) for j in mine]
+    ncl = sum(widths)
+    C = torch.empty(d, ncl + 1, dtype=F64, device=W.device)    # packed owned columns | rhs column
+    off = 0
+    for j, w in zip(mine, widths):
+        C[:, off:off + w].copy_(W[:, nb * j:nb * j + w])
+        off += w
+    C[:, ncl].copy_(W[:, n])
+    n_layout = max(ncl + 1, nb)
+    ws = K.qr_block_workspace(W.device, d, n_layout)
+    panel = torch.empty(d, nb, dtype=F64, device=W.device)
+    tau = torch.empty(nblk * nb, dtype=F64, device=W.device)
+    ranks = dist.get_process_group_ranks(group)
+    for k in range(nblk):
+        owner, kl = k % world, k // world
+        wk = min(nb, n - nb * k)
+        if rank == owner:
+            panel[:, :wk].copy_(C[:, nb * kl:nb * kl + wk])
+        dist.broadcast(panel, src=ranks[owner], group=group)
+        K.qr_factor_block(panel, nb * k, 0, wk, tau[nb * k:], k, n_layout, ws)
+        if rank == owner:
+            C[:, nb * kl:nb * kl + wk].copy_(panel[:, :wk])
+        first = 0 if k < rank else (k - rank) // world + 1     # my blocks with global index <= k
+        c0 = nb * first if first < len(mine) else ncl
+        K.qr_apply_block(d, nb * k, wk, tau[nb * k:], C[:, c0:], n_layout, ws)
+    # assemble R (and keep the rhs column, which every rank carried through all the reflectors)
+    per = (nblk + world - 1) // world * nb
+    send = torch.zeros(n, per, dtype=F64, device=W.device)
+    send[:, :ncl].copy_(C[:n, :ncl])
+    recv = torch.empty(world, n, per, dtype=F64, device=W.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    for r in range(world):
+        off = 0
+        for j in range(r, nblk, world):
+            w = min(nb, n - nb * j)
+            W[:n, nb * j:nb * j + w].copy_(recv[r, :, off:off + w])
+            off += w
+    W[:n, n].copy_(C[:n, ncl])
+    return tau[:n]

@@ -174,6 +174,15 @@ def _sketch(sketch_op_gen, d, A, b, delta, rng, upload=None):
     return S, W
 
 
+def _factor_sketch(W, n, group):
+    """Householder QR of the (replicated) sketch buffer: column-distributed over the ranks when A is row-sharded and
+    the sketch is large enough, the single-GPU factorisation otherwise."""
+    from .. import distla
+    if os.environ.get("PLA_QR_DIST", "1") != "0" and distla.geqrf_distributed_ok(W.shape[0], n, group):
+        return distla.geqrf_distributed(W, n, group)
+    return K.geqrf(W, n)
+
+
 def sso1(A, b, delta, rng, sampling_factor=3, vec_nnz=8, lapack_driver='gelsd'):
     """least_squares.py:108-111."""
     from ..comps.sketchers import oblivious as sko
@@ -286,7 +295,7 @@ class SPO(OverLstsqSolver):
         n = n_cols
         if self.mode == 'qr':
             tic = quick_time()
-            K.geqrf(W, n)                                   # R = triu(W[:n,:n]), W[:, n] = Q^T [b_ske; 0]
+            _factor_sketch(W, n, group)                     # R = triu(W[:n,:n]), W[:, n] = Q^T [b_ske; 0]
             R = W[:n, :n]
             log.time_factor = quick_time() - tic
             tic = quick_time()
@@ -309,7 +318,7 @@ class SPO(OverLstsqSolver):
             # R_qr = U_r diag(sigma) Vh  =>  svd(A_ske) = (Q U_r, sigma, Vh).  Only the n x n SVD goes to
             # cuSOLVER, and U^T b_ske = U_r^T (Q^T b_ske) comes out of the same QR (last column of W).
             tic = quick_time()
-            K.geqrf(W, n)
+            _factor_sketch(W, n, group)
             R, U_r, sigma, Vh = rpc.svd_right_precond(torch.triu(W[:n, :n]))       # :330-339
             log.time_factor = quick_time() - tic
             tic = quick_time()

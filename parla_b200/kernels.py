@@ -460,6 +460,34 @@ def geqrf(W, ncols_factor):
     return tau
 
 
+QR_BLOCK = 128          # column block of the Householder QR (QR_NBO in csrc/qr.cu)
+
+
+def qr_block_workspace(device, M, n_layout):
+    lib = _lib.load()
+    return Workspace.get(device, lib.pla_qr_workspace_bytes(M, n_layout), "qr")
+
+
+def qr_factor_block(P, r0, c0, jb, tau_blk, block_index, n_layout, ws):
+    """Factor columns [c0, c0 + jb) of the row-major P, rows [r0, M), in place (see pla_qr_factor_block_f64)."""
+    _req(P, "P")
+    rc = _lib.load().pla_qr_factor_block_f64(P.data_ptr(), P.shape[0], P.stride(0), int(r0), int(c0), int(jb),
+                                             tau_blk.data_ptr(), int(block_index), int(n_layout), ws.data_ptr(),
+                                             ws.numel(), _stream())
+    _lib.check(rc, "pla_qr_factor_block_f64")
+
+
+def qr_apply_block(M, r0, jb, tau_blk, C, n_layout, ws):
+    """C[r0:, :] <- Q_block^T C[r0:, :] with the reflectors of the last qr_factor_block call (same workspace)."""
+    nc = C.shape[1]
+    if nc == 0:
+        return
+    _req(C, "C")
+    rc = _lib.load().pla_qr_apply_block_f64(int(M), int(r0), int(jb), tau_blk.data_ptr(), C.data_ptr(), C.stride(0), nc,
+                                            int(n_layout), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "pla_qr_apply_block_f64")
+
+
 def orgqr(W, tau, K=None):
     lib = _lib.load()
     M = W.shape[0]
