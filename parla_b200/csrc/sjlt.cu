@@ -103,12 +103,44 @@ __global__ void __launch_bounds__(256) sjlt_fill_kernel(const int32_t* __restric
     }
 }
 
-// sort each destination's segment by packed entry (= by source row): bitonic sort in shared memory
+// sort each bucket by packed entry (= by source row): bitonic sort in shared memory; a bucket longer than the
+// shared-memory buffer (only a contrived operator can produce one: a bucket holds at most one entry per source row
+// of its window) is sorted in place in global memory by the same network in its all-ascending form, where positions
+// past the end act as +infinity and their comparisons are skipped -- never left in atomic (run-dependent) order.
 __global__ void __launch_bounds__(256) sjlt_segsort_kernel(const long long* __restrict__ offsets, int32_t* entries) {
     extern __shared__ int32_t seg[];
     const long long beg = offsets[blockIdx.x], end = offsets[blockIdx.x + 1];
-    const int len = (int)(end - beg);
-    if (len <= 1 || len > SJ_SORT_MAX) return;
+    const long long len64 = end - beg;
+    if (len64 <= 1) return;
+    if (len64 > SJ_SORT_MAX) {
+        int32_t* a = entries + beg;
+        long long np2 = 1;
+        while (np2 < len64) np2 <<= 1;
+        for (long long size = 2; size <= np2; size <<= 1) {
+            const long long half = size >> 1;
+            for (long long i = threadIdx.x; i < np2 / 2; i += blockDim.x) {          // flip stage
+                const long long blk = i / half, off = i - blk * half;
+                const long long lo = blk * size + off, hi = blk * size + size - 1 - off;
+                if (hi < len64) {
+                    const int32_t x = a[lo], y = a[hi];
+                    if (x > y) { a[lo] = y; a[hi] = x; }
+                }
+            }
+            __syncthreads();
+            for (long long stride = half >> 1; stride > 0; stride >>= 1) {           // half-cleaners
+                for (long long i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+                    const long long lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                    if (hi < len64) {
+                        const int32_t x = a[lo], y = a[hi];
+                        if (x > y) { a[lo] = y; a[hi] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
+    const int len = (int)len64;
     int np2 = 1;
     while (np2 < len) np2 <<= 1;
     for (int i = threadIdx.x; i < np2; i += blockDim.x) seg[i] = i < len ? entries[beg + i] : 0x7fffffff;

@@ -6,6 +6,8 @@ DMMA GEMMs followed by an all-reduce(sum) of the small n x k / k x n block, the 
 ``A -= Q B`` is local, and ``orth`` of a row-sharded tall matrix is a Householder TSQR (local QR,
 all-gather of the k x k R factors, QR of the stacked R's, local GEMM).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -67,11 +69,50 @@ def sumsq_all(X):
     return K.sumsq(X.reshape(-1))
 
 
+CHOLQR_MIN_ROWS = 1 << 15       # below this the Householder QR is cheap (and its Q matches LAPACK's signs)
+CHOLQR_MAX_DEFECT = 0.05        # |Q1'Q1 - I|_max after the first round (~ eps cond(Y)^2): second round then reaches eps
+
+
+def _cholqr2(Y, group):
+    """Orthonormal basis of range(Y) for a TALL, numerically well-conditioned Y (m >> k) by two rounds of
+    Cholesky QR: Gram matrix (DMMA GEMM, all-reduced over row shards) -> k x k Cholesky (cuSOLVER glue) ->
+    Q = Y R^{-1} (explicit triangular inverse + DMMA GEMM).  Four GEMM passes over Y instead of the Householder
+    panel sweeps (2^20 x 512: ~70 ms instead of 232 ms).  The first round loses orthogonality as eps cond(Y)^2;
+    that defect is MEASURED (|Q1'Q1 - I|) and the routine returns None -- the caller falls back to Householder --
+    unless it is small enough for the second round to restore orthogonality to machine precision (cond(Y) up to
+    ~1e7).  Rank-deficient or ill-conditioned Y (Cholesky breakdown) also returns None.  The stabiliser of the
+    power iteration (aware.py:160-184) keeps its operand well conditioned, which is the case this is for."""
+    k = Y.shape[1]
+    eye = torch.eye(k, dtype=F64, device=Y.device)
+    Q = Y
+    for rnd in range(2):
+        G = allreduce_(K.gemm(Q, Q, transa=True), group)
+        if rnd == 1 and not float((G - eye).abs().max()) < CHOLQR_MAX_DEFECT:
+            return None
+        R, info = torch.linalg.cholesky_ex(G, upper=True)
+        if int(info) != 0 or not bool(torch.isfinite(R).all()):
+            return None
+        Q = K.gemm(Q, K.trtri_upper(R.contiguous()))
+    return Q
+
+
 def orth(Y):
-    """Orthonormal basis of range(Y): Q factor of a Householder QR (TSQR when row-sharded)."""
+    """Orthonormal basis of range(Y) (``la.qr(Y, mode='economic')[0]``, utils/linalg_wrappers.py:6-7, up to the signs
+    of the columns): CholeskyQR2 for tall well-conditioned operands, Householder QR otherwise (a Householder TSQR
+    when row-sharded)."""
+    Yl = Y.local if isinstance(Y, RowSharded) else Y
+    group = _group(Y) if isinstance(Y, RowSharded) else None
+    rows = Y.shape[0]
+    if (os.environ.get("PLA_CHOLQR", "1") != "0" and Yl.dim() == 2 and rows >= CHOLQR_MIN_ROWS
+            and rows >= 16 * Yl.shape[1] and Yl.shape[0] >= Yl.shape[1]):
+        Q = _cholqr2(Yl if Yl.stride(1) == 1 else Yl.contiguous(), group)
+        if os.environ.get("PLA_TRACE_ORTH"):
+            import sys
+            print(f"[orth] {tuple(Yl.shape)}: {'CholeskyQR2' if Q is not None else 'Householder (fallback)'}", file=sys.stderr)
+        if Q is not None:
+            return _like(Q, Y) if isinstance(Y, RowSharded) else Q
     if not isinstance(Y, RowSharded):
         return K.qr_economic(Y)[0]
-    group = _group(Y)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     k = Y.local.shape[1]
     if Y.local.shape[0] < k:
@@ -122,7 +163,15 @@ def geqrf_distributed_ok(d, n, group):
     return world > 1 and d <= QR_DIST_MAX_ROWS and n >= QR_DIST_MIN_BLOCKS_PER_RANK * K.QR_BLOCK * world
 
 
-def geqrf_distributed(W, n, group):
+class _DeviceBlockQR:
+    """The three block-level kernel calls geqrf_distributed is built from (tests substitute a LAPACK stand-in to
+    check the ownership / packing / collective logic on CPU with gloo)."""
+    workspace = staticmethod(K.qr_block_workspace)
+    factor = staticmethod(K.qr_factor_block)
+    apply = staticmethod(K.qr_apply_block)
+
+
+def geqrf_distributed(W, n, group, _backend=_DeviceBlockQR):
     """In-place Householder QR of the first n columns of W (d x (n + 1), identical on every rank; the last column is
     carried along as a right-hand side), replacing ``la.qr(A_ske)`` + ``Q.T @ b_ske`` (least_squares.py:311,315)
     when A is row-sharded.  After the sketch all-reduce every rank would otherwise repeat the whole factorisation --
@@ -152,7 +201,7 @@ def geqrf_distributed(W, n, group):
         off += w
     C[:, ncl].copy_(W[:, n])
     n_layout = max(ncl + 1, nb)
-    ws = K.qr_block_workspace(W.device, d, n_layout)
+    ws = _backend.workspace(W.device, d, n_layout)
     panel = torch.empty(d, nb, dtype=F64, device=W.device)
     tau = torch.empty(nblk * nb, dtype=F64, device=W.device)
     ranks = dist.get_process_group_ranks(group)
@@ -162,18 +211,19 @@ def geqrf_distributed(W, n, group):
         if rank == owner:
             panel[:, :wk].copy_(C[:, nb * kl:nb * kl + wk])
         dist.broadcast(panel, src=ranks[owner], group=group)
-        K.qr_factor_block(panel, nb * k, 0, wk, tau[nb * k:], k, n_layout, ws)
+        _backend.factor(panel, nb * k, 0, wk, tau[nb * k:], k, n_layout, ws)
         if rank == owner:
             C[:, nb * kl:nb * kl + wk].copy_(panel[:, :wk])
         first = 0 if k < rank else (k - rank) // world + 1     # my blocks with global index <= k
         c0 = nb * first if first < len(mine) else ncl
-        K.qr_apply_block(d, nb * k, wk, tau[nb * k:], C[:, c0:], n_layout, ws)
+        _backend.apply(d, nb * k, wk, tau[nb * k:], C[:, c0:], n_layout, ws)
     # assemble R (and keep the rhs column, which every rank carried through all the reflectors)
     per = (nblk + world - 1) // world * nb
     send = torch.zeros(n, per, dtype=F64, device=W.device)
     send[:, :ncl].copy_(C[:n, :ncl])
-    recv = torch.empty(world, n, per, dtype=F64, device=W.device)
+    recv = torch.empty(world * n, per, dtype=F64, device=W.device)
     dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, n, per)
     for r in range(world):
         off = 0
         for j in range(r, nblk, world):

@@ -249,6 +249,27 @@ def test_sjlt_apply_matches_scipy(K, m, n, d, k):
     assert torch.equal(out, 2 * out2)
 
 
+def test_sjlt_oversized_bucket_is_sorted_not_skipped(K):
+    """A (contrived) operator whose nonzeros pile up in one destination row: the bucket is longer than the shared-
+    memory sort buffer (8192) and is sorted in global memory -- same result on every run, bit for bit."""
+    import scipy.sparse as sps
+    rng = np.random.default_rng(77)
+    m, n, d = 20000, 33, 16
+    rows = np.full((m, 1), 3, dtype=np.int32)
+    rows[::7, 0] = 11
+    signs = rng.choice([-1, 1], size=(m, 1)).astype(np.int8)
+    S = sps.coo_matrix((signs.reshape(-1).astype(float), (rows.reshape(-1), np.arange(m))), shape=(d, m)).tocsc()
+    A = rng.standard_normal((m, n))
+    outs = []
+    for _ in range(3):
+        plan = K.SjltPlan(dev(rows), dev(signs), d, validate=True)
+        out = torch.empty(d, n, dtype=torch.float64, device="cuda")
+        plan.apply(dev(A), 1.0, out)
+        outs.append(out)
+    assert rel(outs[0], S @ A) < 1e-13
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
 def test_sjlt_plan_rejects_bad_indices(K):
     rows = dev(np.array([[0, 7], [1, 2]], dtype=np.int32))
     signs = dev(np.ones((2, 2), dtype=np.int8))

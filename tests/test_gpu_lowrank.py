@@ -116,6 +116,40 @@ def test_qb_properties_native_operators(rla, shape, rank, which):
         assert torch.equal(Ad.cpu(), torch.from_numpy(A))                 # test_unchanged_A
 
 
+def test_orth_tall_cholqr2_and_fallback(rla):
+    """orth of a tall operand: CholeskyQR2 when well conditioned (orthonormal to machine precision, same range),
+    Householder when the first round's orthogonality defect says otherwise (ill-conditioned / rank-deficient)."""
+    from parla_b200 import distla
+    g = torch.Generator(device="cuda").manual_seed(4)
+    m, k = 1 << 16, 96
+    Y = torch.randn(m, k, dtype=torch.float64, device="cuda", generator=g) * torch.logspace(0, -3, k, dtype=torch.float64, device="cuda")
+    assert distla._cholqr2(Y, None) is not None
+    Q = rla.orth(Y)
+    eye = torch.eye(k, dtype=torch.float64, device="cuda")
+    assert float(torch.linalg.norm(Q.T @ Q - eye)) < 1e-13
+    assert float(torch.linalg.norm(Y - Q @ (Q.T @ Y)) / torch.linalg.norm(Y)) < 1e-13          # same range
+    # (a bad COLUMN SCALING alone does not hurt Cholesky QR; an ill-conditioned mixing of the columns does)
+    Qk = torch.linalg.qr(torch.randn(k, k, dtype=torch.float64, device="cuda", generator=g)).Q
+    Y0 = torch.randn(m, k, dtype=torch.float64, device="cuda", generator=g)
+    Yb = Y0 @ ((Qk * torch.logspace(0, -11, k, dtype=torch.float64, device="cuda")) @ Qk.T)       # cond ~ 1e11
+    assert distla._cholqr2(Yb, None) is None
+    Qb = rla.orth(Yb)
+    assert float(torch.linalg.norm(Qb.T @ Qb - eye)) < 1e-12
+    Yr = Y.clone()
+    Yr[:, -3:] = Yr[:, :3]                                                                        # rank k - 3
+    assert distla._cholqr2(Yr, None) is None
+    Qr = rla.orth(Yr)
+    assert float(torch.linalg.norm(Qr.T @ Qr - eye)) < 1e-12
+    # the driver on a tall matrix (fast path inside RS1 / RF1 / QB1) against the live oracle
+    A = orc.exponent_spectrum(1 << 16, 256, 200, np.random.default_rng(8), 20.0)
+    alg = lambda lib, orth: lib.SVD1(lib.QB1(lib.RF1(lib.RS1(orc.SkOpGA(), 2, orth, 1))))
+    U, s, Vh = alg(rla, rla.orth)(dev(A), 48, np.nan, 0, np.random.default_rng(7))
+    Uo, so, Vho = alg(orc, orc.orth)(A, 48, np.nan, 0, np.random.default_rng(7))
+    assert np.max(np.abs(s.cpu().numpy() - so)) <= 1e-10 * so[0]
+    approx = (U * s) @ Vh
+    assert np.linalg.norm(approx.cpu().numpy() - (Uo * so) @ Vho) <= 1e-10 * np.linalg.norm(A)
+
+
 def test_qb2_tolerance_and_overwrite(rla):
     A = orc.exponent_spectrum(300, 120, 100, np.random.default_rng(3), 4.0)
     rf = rla.RF1(rla.RS1(rla.SkOpGA(), 0, rla.orth, 1))

@@ -112,6 +112,67 @@ def test_row_sharded_allreduce_gloo_world2():
     assert list(out) == [1, 1]
 
 
+class _LapackBlockQR:
+    """CPU stand-in for the block-level QR kernels (torch.geqrf / ormqr): same contract, state kept in `ws`."""
+
+    @staticmethod
+    def workspace(device, d, n_layout):
+        return {}
+
+    @staticmethod
+    def factor(panel, r0, c0, jb, tau_blk, k, n_layout, ws):
+        a, tau = torch.geqrf(panel[r0:, c0:c0 + jb].clone())
+        panel[r0:, c0:c0 + jb] = a
+        tau_blk[:jb] = tau
+        ws["a"], ws["tau"] = a, tau
+
+    @staticmethod
+    def apply(d, r0, jb, tau_blk, C, n_layout, ws):
+        if C.shape[1]:
+            C[r0:, :] = torch.ormqr(ws["a"], ws["tau"], C[r0:, :].clone(), left=True, transpose=True)
+
+
+def _qr_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from parla_b200 import distla
+        ok = True
+        for d, n in ((700, 300), (600, 513), (1100, 1024)):       # partial last block, odd block counts per rank
+            g = torch.Generator().manual_seed(5)
+            W0 = torch.randn(d, n + 1, dtype=torch.float64, generator=g)
+            W = W0.clone()
+            tau = distla.geqrf_distributed(W, n, dist.group.WORLD, _backend=_LapackBlockQR)
+            a_ref, tau_ref = torch.geqrf(W0[:, :n].clone())
+            R_ref = torch.triu(a_ref[:n])
+            qtb_ref = torch.ormqr(a_ref, tau_ref, W0[:, n:n + 1].clone(), left=True, transpose=True)[:n, 0]
+            ok = ok and torch.allclose(torch.triu(W[:n, :n]), R_ref, rtol=0, atol=1e-11)
+            ok = ok and torch.allclose(W[:n, n], qtb_ref, rtol=0, atol=1e-11)
+            ok = ok and torch.allclose(tau, tau_ref, rtol=0, atol=1e-12)
+        assert not distla.geqrf_distributed_ok(50000, 4096, dist.group.WORLD)      # too many rows for the block kernel
+        assert not distla.geqrf_distributed_ok(8192, 300, dist.group.WORLD)        # too few blocks per rank
+        assert distla.geqrf_distributed_ok(8192, 2048, dist.group.WORLD)
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_distributed_qr_logic_gloo_world2():
+    """Ownership, packing, panel broadcast and the final all-gather of distla.geqrf_distributed, with LAPACK standing
+    in for the three block kernels (world_size 2, gloo, CPU)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    port_ = _free_port()
+    procs = [ctx.Process(target=_qr_worker, args=(r, world, port_, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert list(out) == [1, 1]
+
+
 def test_saddle_and_srct_public_names():
     for name in ("SPS1", "SPS2", "sps", "SaddleSolver", "PcSS1", "PcSS2", "pcss1", "pcss2", "pcg", "SPU1",
                  "SkOpTC", "srct_operator", "generate_srct", "apply_srct", "QB3", "EVD2", "SkOpSS", "SkOpON", "SkOpIN",
