@@ -13,7 +13,7 @@
 
 namespace pla {
 
-constexpr int SP_GROUP_MAX = 256;     // consumer threads per group: 256 (8 warps) or, for narrow A, 128
+constexpr int SP_GROUP_MAX = 512;     // consumer threads per group: 256 (8 warps); 128 for narrow A; 512 for the widest rows
 constexpr int SP_RMAX = 16;           // max rows per tile (16 for matrices of <= 256 columns: 32 KB tiles)
 constexpr int SP_MAX_STAGES = 8;
 constexpr int SP_MAX_GROUPS = 4;
@@ -397,13 +397,13 @@ extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_
         else if (groups <= 2) { if (two) PLA_SP_CASE(2, 2, 2, 256); else PLA_SP_CASE(2, 2, 1, 256); }
         else if (groups <= 4) { if (two) PLA_SP_CASE(2, 4, 2, 256); else PLA_SP_CASE(2, 4, 1, 256); }
         else if (groups <= 8) PLA_SP_CASE(2, 8, 1, 256);
-        else PLA_SP_CASE(2, 16, 1, 256);
+        else PLA_SP_CASE(2, 8, 1, 512);              // 4096 < n <= 8192: one group of 16 warps, 16 columns per thread
     } else {
         if (groups <= 1) { if (two) PLA_SP_CASE(1, 1, 2, 256); else PLA_SP_CASE(1, 1, 1, 256); }
         else if (groups <= 2) { if (two) PLA_SP_CASE(1, 2, 2, 256); else PLA_SP_CASE(1, 2, 1, 256); }
         else if (groups <= 4) { if (two) PLA_SP_CASE(1, 4, 2, 256); else PLA_SP_CASE(1, 4, 1, 256); }
         else if (groups <= 8) PLA_SP_CASE(1, 8, 1, 256);
-        else PLA_SP_CASE(1, 16, 1, 256);
+        else PLA_SP_CASE(1, 8, 1, 512);
     }
 #undef PLA_SP_CASE
     if (e != cudaSuccess) { set_error("pla_stream_pass_f64: launch failed: %s", cudaGetErrorString(e)); return (int)e; }

@@ -319,10 +319,21 @@ class SPO(OverLstsqSolver):
             # cuSOLVER, and U^T b_ske = U_r^T (Q^T b_ske) comes out of the same QR (last column of W).
             tic = quick_time()
             _factor_sketch(W, n, group)
-            R, U_r, sigma, Vh = rpc.svd_right_precond(torch.triu(W[:n, :n]))       # :330-339
-            log.time_factor = quick_time() - tic
-            tic = quick_time()
-            z_ske = K.rmatvec(U_r, W[:n, n].contiguous())[:R.shape[1]].clone()      # U[:d].T @ b_ske
+            X = None
+            if n >= rpc.FAST_SVD_MIN_N and rpc.FAST_SVD:
+                # full numerical rank with a wide margin: R_qr^{-1} = (V / sigma) U_r^T is the SVD preconditioner up
+                # to an orthogonal factor on the right -- same x, same error history, no n x n decomposition
+                X = rpc.inverse_if_well_conditioned(W[:n, :n])
+            if X is not None:
+                R = X
+                log.time_factor = quick_time() - tic
+                tic = quick_time()
+                z_ske = W[:n, n].contiguous()
+            else:
+                R, U_r, sigma, Vh = rpc.svd_right_precond(torch.triu(W[:n, :n]))   # :330-339
+                log.time_factor = quick_time() - tic
+                tic = quick_time()
+                z_ske = K.rmatvec(U_r, W[:n, n].contiguous())[:R.shape[1]].clone()  # U[:d].T @ b_ske
             tri = False
         else:
             raise ValueError()
