@@ -69,6 +69,10 @@ int pla_trsv_upper_f64(const double* R, int64_t n, int64_t ldr, int trans, const
  * applied with pla_stream_pass_f64, which turns the two sequential solves per LSQR iteration
  * (preconditioning.py:28,37) into two bandwidth-bound matvecs over an L2-resident matrix.        */
 int pla_trtri_diag_f64(const double* R, int64_t n, int64_t ldr, double* X, int64_t ldx, void* stream);
+/* One recursion level of the triangular inverse for small blocks, every pair of the level in one launch: with the
+ * s x s diagonal blocks of X already inverted (s = 32 after pla_trtri_diag_f64, then 64), X12 = -X11 (R12 X22).
+ * Larger levels are DMMA GEMMs (pla_gemm_f64).                                                        */
+int pla_trtri_merge_f64(const double* R, int64_t n, int64_t ldr, double* X, int64_t ldx, int64_t s, void* stream);
 
 /* ---------------------------------------------------------------- LSQR recurrences on device
  * Replaces the scalar/vector part of parla/comps/determiter/lsqr.py:342-395 (init) and :412-526

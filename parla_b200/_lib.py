@@ -25,6 +25,7 @@ SIGNATURES = {
                                     c_vp, c_vp, c_sz, c_vp]),
     "pla_trsv_upper_f64": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "pla_trtri_diag_f64": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "pla_trtri_merge_f64": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),
     "pla_lsqr_init_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_vp]),
     "pla_lsqr_step_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

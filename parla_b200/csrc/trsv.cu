@@ -131,9 +131,68 @@ __global__ void __launch_bounds__(TI_BS) trtri_diag_kernel(const double* __restr
         if (j < bs) X[(i0 + r) * ldx + i0 + j] = Xb[r][j];
 }
 
+// One level of the recursion for SMALL blocks, all pairs of the level in ONE launch: with the s x s diagonal blocks
+// X11, X22 already inverted, X12 = -X11 (R12 X22).  CTA <-> pair; the three blocks live in shared memory.  (Issued as
+// individual GEMMs from the host the levels s = 32, 64 cost ~100 launches of a few microseconds each.)
+constexpr int TM_THREADS = 256;
+__global__ void __launch_bounds__(TM_THREADS) trtri_merge_kernel(const double* __restrict__ R, long long n, long long ldr,
+                                                                 double* X, long long ldx, int s) {
+    extern __shared__ double tm_smem[];
+    const int ld = s + 1;
+    double* X11 = tm_smem;                 // s x s upper triangular
+    double* R12 = X11 + s * ld;            // s x w
+    double* X22 = R12 + s * ld;            // w x w upper triangular   (then T = R12 X22 overwrites R12)
+    const long long i0 = (long long)blockIdx.x * 2 * s, i1 = i0 + s;
+    if (i1 >= n) return;
+    const int w = (int)min((long long)s, n - i1);
+    for (int idx = threadIdx.x; idx < s * s; idx += TM_THREADS) {
+        const int r = idx / s, c = idx - r * s;
+        X11[r * ld + c] = (c >= r) ? X[(i0 + r) * ldx + i0 + c] : 0.0;
+        R12[r * ld + c] = (c < w) ? R[(i0 + r) * ldr + i1 + c] : 0.0;
+        X22[r * ld + c] = (r < w && c < w && c >= r) ? X[(i1 + r) * ldx + i1 + c] : 0.0;
+    }
+    __syncthreads();
+    // T = R12 X22 (X22 upper triangular: l <= c); every thread keeps its outputs in registers until all are computed
+    double t[16];
+    int cnt = 0;
+    for (int idx = threadIdx.x; idx < s * w; idx += TM_THREADS, ++cnt) {
+        const int r = idx / w, c = idx - r * w;
+        double acc = 0.0;
+        for (int l = 0; l <= c; ++l) acc = fma(R12[r * ld + l], X22[l * ld + c], acc);
+        t[cnt] = acc;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int idx = threadIdx.x; idx < s * w; idx += TM_THREADS, ++cnt) {
+        const int r = idx / w, c = idx - r * w;
+        R12[r * ld + c] = t[cnt];
+    }
+    __syncthreads();
+    // X12 = -X11 T (X11 upper triangular: l >= r)
+    for (int idx = threadIdx.x; idx < s * w; idx += TM_THREADS) {
+        const int r = idx / w, c = idx - r * w;
+        double acc = 0.0;
+        for (int l = r; l < s; ++l) acc = fma(X11[r * ld + l], R12[l * ld + c], acc);
+        X[(i0 + r) * ldx + i1 + c] = -acc;
+    }
+}
+
 }  // namespace pla
 
 using namespace pla;
+
+extern "C" int pla_trtri_merge_f64(const double* R, int64_t n, int64_t ldr, double* X, int64_t ldx, int64_t s, void* stream) {
+    PLA_CHECK_ARG(R != nullptr, 1, "R is null");
+    PLA_CHECK_ARG(n >= 1 && ldr >= n, 3, "bad n / ldr");
+    PLA_CHECK_ARG(X != nullptr && ldx >= n, 4, "bad X / ldx");
+    PLA_CHECK_ARG(s == 32 || s == 64, 6, "level size must be 32 or 64");
+    const long long pairs = (n + 2 * s - 1) / (2 * s);
+    const size_t smem = (size_t)3 * s * (s + 1) * sizeof(double);
+    PLA_CUDA(cudaFuncSetAttribute(trtri_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    trtri_merge_kernel<<<(unsigned)pairs, TM_THREADS, smem, (cudaStream_t)stream>>>(R, n, ldr, X, ldx, (int)s);
+    PLA_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int pla_trtri_diag_f64(const double* R, int64_t n, int64_t ldr, double* X, int64_t ldx, void* stream) {
     PLA_CHECK_ARG(R != nullptr, 1, "R is null");

@@ -204,6 +204,10 @@ def trtri_upper(R):
     X = torch.zeros(n, n, dtype=F64, device=R.device)
     _lib.check(lib.pla_trtri_diag_f64(R.data_ptr(), n, R.stride(0), X.data_ptr(), n, _stream()), "pla_trtri_diag_f64")
     s = 32
+    while s < n and s <= 64:          # small levels: every pair of the level in one launch
+        _lib.check(lib.pla_trtri_merge_f64(R.data_ptr(), n, R.stride(0), X.data_ptr(), n, s, _stream()),
+                   "pla_trtri_merge_f64")
+        s *= 2
     while s < n:
         for i0 in range(0, n, 2 * s):
             i1, i2 = i0 + s, min(i0 + 2 * s, n)

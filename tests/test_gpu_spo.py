@@ -111,6 +111,25 @@ def test_spo_svd_rank_deficient_matches_reference(rla, name):
             assert abs(log.errors[0] - fx["errors"][0]) <= 1e-9 * fx["errors"][0]
 
 
+def test_lsqr_iteration_as_cuda_graph_gives_identical_results(rla):
+    """The optional CUDA-graph replay of the LSQR iteration (PLA_LSQR_GRAPH=1; off by default because it measured
+    slower) must be bit-identical to the eager loop: same kernels, same order, same buffers."""
+    from parla_b200.comps.determiter import lsqr as lsqr_mod
+    rng = np.random.default_rng(17)
+    A = rng.standard_normal((20000, 120)) * np.logspace(0, 3, 120)
+    b = rng.standard_normal(20000)
+    Ad, bd = dev(A), dev(b)
+    for delta in (0.0, 0.3):
+        x_eager, log_eager = rla.SAP1(rla.SkOpSJ(8), 4)(Ad, bd, delta, 1e-12, 100, 3)
+        lsqr_mod.USE_GRAPH = True
+        try:
+            x_graph, log_graph = rla.SAP1(rla.SkOpSJ(8), 4)(Ad, bd, delta, 1e-12, 100, 3)
+        finally:
+            lsqr_mod.USE_GRAPH = False
+        assert torch.equal(x_eager, x_graph) and np.array_equal(log_eager.errors, log_graph.errors)
+        assert log_graph.passes_over_A == log_eager.passes_over_A
+
+
 def test_sap1_sap2_are_spo_modes(rla):
     """CHANGELOG.md:57 names: SAP1 == SPO(mode='qr'), SAP2 == SPO(mode='svd'); bit-identical results."""
     rng = np.random.default_rng(21)
