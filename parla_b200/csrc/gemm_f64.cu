@@ -157,6 +157,25 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // beta != 0: the accumulators START at (beta / alpha) C, so the 64 loads of C per thread are in flight together
+    // with the first operand tiles and the epilogue only stores alpha * acc.  (Reading C in the epilogue serialised
+    // 64 load -> fma -> store round trips per thread: the K = 128 block-reflector update of the QR ran at 12-20 TF.)
+    const bool c_in_acc = p.part == nullptr && p.beta != 0.0 && p.alpha != 0.0;
+    if (c_in_acc) {
+        const double f = p.beta / p.alpha;
+        const int fr0 = lane >> 2, fc0 = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long gm = m0 + wm * 64 + i * 8 + fr0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long gn = n0 + wn * 32 + j * 8 + 2 * fc0;
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (gm < p.M && gn + e < p.N) acc[i][j][e] = f * p.C[gm * p.ldc + gn + e];
+            }
+        }
+    }
 
     // The two operand tiles of a k-step are fetched by separate helpers so that their address /
     // predicate / Philox instructions can be interleaved with DMMA groups (tensor pipe stays busy).
@@ -229,7 +248,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
                 if (gn + e < p.N) {
                     double* dst = out + gm * ldo + gn + e;
                     if (split) *dst = acc[i][j][e];
-                    else *dst = (p.beta == 0.0) ? p.alpha * acc[i][j][e] : fma(p.alpha, acc[i][j][e], p.beta * *dst);
+                    else if (c_in_acc || p.beta == 0.0) *dst = p.alpha * acc[i][j][e];
+                    else *dst = fma(p.alpha, acc[i][j][e], p.beta * *dst);
                 }
             }
         }
@@ -330,6 +350,23 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gauss_sketch_kernel(const GemmP
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    const bool c_in_acc = p.part == nullptr && p.beta != 0.0 && p.alpha != 0.0;     // see gemm_f64_kernel
+    if (c_in_acc) {
+        const double f = p.beta / p.alpha;
+        const int fr0 = lane >> 2, fc0 = lane & 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long gm = m0 + i * 8 + fr0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long gn = n0 + wn * 32 + j * 8 + 2 * fc0;
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (gm < p.M && gn + e < p.N) acc[i][j][e] = f * p.C[gm * p.ldc + gn + e];
+            }
+        }
+    }
+
     Philox4 words{0u, 0u, 0u, 0u};
     auto gen_words = [&](int kt_local) { words = gs_gen_words(p.seed, p.col_offset, m0, (kt_begin + kt_local) * GM_BK); };
     auto gen_store = [&](int kt_local) {
@@ -388,7 +425,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gauss_sketch_kernel(const GemmP
                 if (gn + e < p.N) {
                     double* dst = out + gm * ldo + gn + e;
                     if (split) *dst = acc[i][j][e];
-                    else *dst = (p.beta == 0.0) ? p.alpha * acc[i][j][e] : fma(p.alpha, acc[i][j][e], p.beta * *dst);
+                    else if (c_in_acc || p.beta == 0.0) *dst = p.alpha * acc[i][j][e];
+                    else *dst = fma(p.alpha, acc[i][j][e], p.beta * *dst);
                 }
             }
         }
