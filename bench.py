@@ -393,6 +393,7 @@ def run_gpu_arm(a):
     numa = numa_pin_for_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    dmma_burst = dmma_peak(dev) if (rank == 0 and not a.no_extras) else None      # idle, cool GPU: burst clocks
 
     def barrier():
         if world > 1:
@@ -493,7 +494,10 @@ def run_gpu_arm(a):
         extras["gauss"] = {"kernel": "pla::gauss_sketch_kernel (S tiles generated in shared memory from Philox4x32-10, DMMA.8x8x4)",
                            "sketch_s": tg, "flops": flops, "achieved": flops / tg / 1e12, "unit": "TFLOP/s",
                            "peak": pk, "frac": flops / tg / 1e12 / pk, "bound": "tensor (FP64 DMMA)",
-                           "peak_source": "pla_dmma_probe measured live in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                           "peak_source": "pla_dmma_probe measured live right before the sketch, i.e. on the hot, power-capped GPU "
+                                          "(MEASURED_PEAKS.json has no FP64 figure); peak_burst is the same probe on the idle GPU at "
+                                          "the start of the run",
+                           "peak_burst": dmma_burst, "frac_of_burst": flops / tg / 1e12 / dmma_burst if dmma_burst else None,
                            "sjlt_sketch_s_same_A": phases["sketch"]}
         del W, op
 
@@ -543,6 +547,7 @@ def run_gpu_arm(a):
     else:
         del A, b, Ash, bsh
     alg.last_residual = None
+    alg.iterative_solver.last_op = None
     x = log = None
     K.Workspace._bufs.clear()
     torch.cuda.empty_cache()

@@ -383,6 +383,7 @@ class SPO(OverLstsqSolver):
             log.iters = int(np.atleast_1d(iter_errors).size)
             log.passes_over_A = op.passes + 1      # + the sketch
         self.last_residual = res[1]
+        self.iterative_solver.last_op = None     # (it references A: do not keep a 64 GiB upload alive after the call)
         x = res[0]
         return _to_host(x, host), log
 
