@@ -19,6 +19,21 @@ def svd1(A, k, over, tol, inner_num_pass, block_size, rng):
     return SVD1(QB2(RF1(rso_), block_size, overwrite_a=False))(A, k, tol, over, rng)
 
 
+def _svd_of_wide(B):
+    """Thin SVD of the (k + over) x n factor B (``la.svd(B, full_matrices=False)``, svd.py:164).  For a wide B
+    (n >= 4 rows) it goes through the Householder QR of B^T (hand-written kernels): B^T = Q_b R_b, R_b^T = U s W^T
+    (the only cuSOLVER call left is this k x k SVD) and Vh = (Q_b W)^T -- backward stable like the direct SVD, and
+    the 512 x 16384 factor of BASELINE configs[3] no longer goes through cuSOLVER's gesvd as a whole."""
+    from .. import kernels as K
+    kk, n = B.shape
+    if n < 4 * kk or kk < 32:
+        return torch.linalg.svd(B, full_matrices=False)
+    Qb, Rb = K.qr_economic(B.T.contiguous())                   # n x kk, kk x kk
+    U, s, Wh = torch.linalg.svd(Rb.T.contiguous(), full_matrices=False)
+    Vh = K.gemm(Wh.contiguous(), Qb, transb=True)              # (Q_b W)^T = W^T Q_b^T
+    return U, s, Vh
+
+
 class SVDecomposer:
 
     def __call__(self, A, k, tol, over, rng):
@@ -35,8 +50,7 @@ class SVD1(SVDecomposer):
     def __call__(self, A, k, tol, over, rng):
         rng = np.random.default_rng(rng)
         Q, B = self.qb(A, k + over, tol, rng)
-        # small dense SVD of the (k+over) x n factor: cuSOLVER glue
-        U, s, Vh = torch.linalg.svd(B.contiguous(), full_matrices=False)
+        U, s, Vh = _svd_of_wide(B.contiguous())
         if over > 0:                                               # svd.py:165-169
             cutoff = min(k, s.numel())
             U, s, Vh = U[:, :cutoff], s[:cutoff], Vh[:cutoff, :]
