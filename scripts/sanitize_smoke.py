@@ -48,5 +48,36 @@ for gen in (rla.SkOpSJ(8), rla.SkOpGA()):
 nys = rla.SPS1(rla.SkOpGA(), 0.8)
 x, yv, log = nys(dev(A), dev(b), dev(c), 0.2, 1e-12, 60, 1, logging=True)
 assert np.linalg.norm(x.cpu().numpy() - ref) < 1e-8 * np.linalg.norm(ref)
+# ---- round 2 additions: cooperative block QR (all-to-all and fan-out exchanges, partial last block), batched trtri
+#      levels, wide / 512-thread streaming pass, GEMM with beta folded into the accumulators, oversized SJLT bucket,
+#      rank-truncated SVD mode, CholeskyQR2
+for (m, n) in ((2600, 300), (1300, 141)):
+    Y = rng.standard_normal((m, n))
+    Q, Rr = K.qr_economic(dev(Y))
+    assert np.allclose((Q @ Rr).cpu().numpy(), Y)
+R2 = np.linalg.qr(rng.standard_normal((400, 200)))[1]
+assert np.allclose(K.trtri_upper(dev(R2)).cpu().numpy() @ R2, np.eye(200), atol=1e-9)
+for (m, n) in ((40, 8448), (60, 8192), (50, 4099)):
+    A2, w2, u2 = rng.standard_normal((m, n)), rng.standard_normal(n), rng.standard_normal(m)
+    ud = dev(u2)
+    z = K.stream_pass(dev(A2), w=dev(w2), u=ud, sa=0.5, su=-1.0, flags=3).cpu().numpy()
+    ur = 0.5 * (A2 @ w2) - u2
+    assert np.allclose(ud.cpu().numpy(), ur) and np.allclose(z[:n], A2.T @ ur)
+Cm = rng.standard_normal((150, 70)); Am = rng.standard_normal((150, 90)); Bm = rng.standard_normal((90, 70))
+Cd = dev(Cm)
+K.gemm(dev(Am), dev(Bm), alpha=-1.0, beta=1.0, out=Cd)
+assert np.allclose(Cd.cpu().numpy(), Cm - Am @ Bm)
+rows = np.full((9000, 1), 2, dtype=np.int32); signs = np.ones((9000, 1), dtype=np.int8)
+plan = K.SjltPlan(dev(rows), dev(signs), 8, validate=True)
+outp = torch.empty(8, 5, dtype=torch.float64, device="cuda")
+A3 = rng.standard_normal((9000, 5))
+plan.apply(dev(A3), 1.0, outp)
+assert np.allclose(outp.cpu().numpy()[2], A3.sum(axis=0))
+Ald = rng.standard_normal((400, 6)) @ rng.standard_normal((6, 12))
+x, log = rla.SAP2(rla.SkOpGA(), 3)(dev(Ald), dev(Ald @ rng.standard_normal(12)), 0.0, 1e-12, 50, 2)
+assert np.all(np.isfinite(x.cpu().numpy()))
+Yt = torch.randn(1 << 15, 24, dtype=torch.float64, device="cuda")
+Qt = rla.orth(Yt)
+assert float(torch.linalg.norm(Qt.T @ Qt - torch.eye(24, dtype=torch.float64, device="cuda"))) < 1e-12
 torch.cuda.synchronize()
 print("sanitize_smoke OK")
