@@ -132,6 +132,10 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool
     int sz = pred ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(sz) : "memory");
 }
+// 16-byte slot, `bytes` (0, 8 or 16) read from global and the rest zero-filled: the last chunk of an odd-length row
+__device__ __forceinline__ void cp_async16_n(void* dst_smem, const void* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -38,19 +38,23 @@ struct GemmParams {
 // Each thread copies the same (row, chunk) slots of every k-tile, so addresses are one base pointer
 // plus compile-time multiples of the leading dimension and the bounds tests are hoisted.
 // Source stored [X][K] (k contiguous): smem tile[x][GM_LDK].   rows x0.., cols k0..
-template <bool VEC16>
+// VEC16: 0 = 8-byte copies; 1 = 16-byte copies, even extent along the contiguous axis; 2 = 16-byte copies whose last
+// slot of an odd-length row is half filled (cp.async src-size 8).  (2 costs a select per copy: 5 % on the big products.)
+template <int VEC16>
 __device__ __forceinline__ void load_xk(double* tile, const double* __restrict__ src, long long ld, long long X,
                                         long long K, long long x0, long long k0) {
     const int tid = threadIdx.x;
     if (VEC16) {                       // 128 rows x 8 chunks(16B): thread -> chunk tid&7 of rows (tid>>3) + 32 i
         const int r0 = tid >> 3, c2 = 2 * (tid & 7);
+        const int kbytes = (VEC16 == 1 || k0 + c2 + 1 < K) ? 16 : 8;
         const bool kok = k0 + c2 < K;
         const double* p = src + (x0 + r0) * ld + k0 + c2;
         double* d = tile + r0 * GM_LDK + c2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const bool ok = kok && (x0 + r0 + 32 * i < X);
-            cp_async16(d + 32 * i * GM_LDK, ok ? p + 32 * i * ld : src, ok);
+            if (VEC16 == 1) cp_async16(d + 32 * i * GM_LDK, ok ? p + 32 * i * ld : src, ok);
+            else cp_async16_n(d + 32 * i * GM_LDK, ok ? p + 32 * i * ld : src, ok ? kbytes : 0);
         }
     } else {                           // 128 rows x 16 doubles: thread -> column tid&15 of rows (tid>>4) + 16 i
         const int r0 = tid >> 4, c = tid & 15;
@@ -66,7 +70,7 @@ __device__ __forceinline__ void load_xk(double* tile, const double* __restrict__
 }
 // Source stored [K][X] (x contiguous): smem tile[k][GM_LDX].  `xcol` (optional, length K) is a
 // logical extra column at index X (used to sketch [A | b] in one launch).
-template <bool VEC16>
+template <int VEC16>
 __device__ __forceinline__ void load_kx(double* tile, const double* __restrict__ src, long long ld, long long X,
                                         long long K, long long x0, long long k0,
                                         const double* __restrict__ xcol = nullptr) {
@@ -74,6 +78,7 @@ __device__ __forceinline__ void load_kx(double* tile, const double* __restrict__
     if (VEC16) {                       // 16 rows x 64 chunks(16B): thread -> chunk tid&63 of rows (tid>>6) + 4 i
         const int r0 = tid >> 6, c2 = 2 * (tid & 63);
         const long long gx = x0 + c2;
+        const int xbytes = (VEC16 == 1 || gx + 1 < X) ? 16 : 8;               // odd X (xcol == null): half a slot
         const bool xok = gx < X;
         const bool extra = (xcol != nullptr) && (gx == X);
         const double* p = src + (k0 + r0) * ld + gx;
@@ -83,7 +88,8 @@ __device__ __forceinline__ void load_kx(double* tile, const double* __restrict__
             const bool kok = k0 + r0 + 4 * i < K;
             if (!extra) {
                 const bool ok = xok && kok;
-                cp_async16(d + 4 * i * GM_LDX, ok ? p + 4 * i * ld : src, ok);
+                if (VEC16 == 1) cp_async16(d + 4 * i * GM_LDX, ok ? p + 4 * i * ld : src, ok);
+                else cp_async16_n(d + 4 * i * GM_LDX, ok ? p + 4 * i * ld : src, ok ? xbytes : 0);
             } else {
                 cp_async8(d + 4 * i * GM_LDX, kok ? xcol + k0 + r0 + 4 * i : src, kok);
                 cp_async8(d + 4 * i * GM_LDX + 1, src, false);
@@ -138,7 +144,10 @@ __device__ __forceinline__ void gen_xk(double* tile, uint64_t seed, long long co
 
 // TA: 0 = A stored [M][K], 1 = A stored [K][M], 2 = generated Gaussian operator.
 // TB: 0 = B stored [K][N], 1 = B stored [N][K].
-template <int TA, int TB, bool VEC16>
+// CACC: the beta != 0 update C = alpha op(A) op(B) + beta C without split-K, with a prologue / epilogue built for it
+// (the rank-128 block-reflector update of the QR).  It is a separate instantiation because any change to the
+// prologue / epilogue code perturbs ptxas' schedule of the main loop of the other variants by +-5 %.
+template <int TA, int TB, int VEC16, bool CACC>
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParams p) {
     extern __shared__ __align__(16) double gm_smem[];
     double* sA = gm_smem;                               // [STAGES][GM_TILE]
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
     // with the first operand tiles and the epilogue only stores alpha * acc.  (Reading C in the epilogue serialised
     // 64 load -> fma -> store round trips per thread: the K = 128 block-reflector update of the QR ran at 12-20 TF.)
     const bool c_in_acc = p.part == nullptr && p.beta != 0.0 && p.alpha != 0.0;
-    if (c_in_acc) {
+    if (!CACC && c_in_acc) {
         const double f = p.beta / p.alpha;
         const int fr0 = lane >> 2, fc0 = lane & 3;
 #pragma unroll
@@ -173,6 +182,45 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     if (gm < p.M && gn + e < p.N) acc[i][j][e] = f * p.C[gm * p.ldc + gn + e];
+            }
+        }
+    }
+    // CACC: interior tiles (the CTA-uniform common case) use unpredicated, 16-byte accesses when C allows them: with
+    // per-element predicates ptxas issued the loads in small dependent groups (14 us per tile against a 19 us main loop).
+    const bool interior = (m0 + GM_BM <= p.M) && (n0 + GM_BN <= p.N);
+    const bool c_vec = interior && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.ldc & 1) == 0);
+    const long long c_off = (m0 + wm * 64 + (lane >> 2)) * p.ldc + n0 + wn * 32 + 2 * (lane & 3);   // fragment (0, 0)
+    if (CACC) {
+        if (c_vec) {
+            const double* cp = p.C + c_off;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 v = *reinterpret_cast<const double2*>(cp + (long long)(i * 8) * p.ldc + j * 8);
+                    acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+                }
+        } else if (interior) {
+            const double* cp = p.C + c_off;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j][0] = cp[(long long)(i * 8) * p.ldc + j * 8];
+                    acc[i][j][1] = cp[(long long)(i * 8) * p.ldc + j * 8 + 1];
+                }
+        } else {
+            const int fr0 = lane >> 2, fc0 = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long gm = m0 + wm * 64 + i * 8 + fr0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long gn = n0 + wn * 32 + j * 8 + 2 * fc0;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (gm < p.M && gn + e < p.N) acc[i][j][e] = p.C[gm * p.ldc + gn + e];
+                }
             }
         }
     }
@@ -198,6 +246,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
     for (int s = 0; s < GM_STAGES - 1; ++s) {
         if (s < nkt) { issue_a(s, -1); issue_b(s); }
         cp_async_commit();
+    }
+    if (CACC) {                                          // scale once the operand copies are on their way
+        const double f = p.beta / p.alpha;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] *= f; acc[i][j][1] *= f; }
     }
     const int fr = lane >> 2, fc = lane & 3;            // fragment row / k (A), k / col (B)
     for (int kt = 0; kt < nkt; ++kt) {
@@ -233,6 +288,42 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
     cp_async_wait<0>();
 
     // ---- epilogue: lane holds C[m][n..n+1], m = fr, n = 2*fc within each 8x8 fragment
+    if (CACC) {
+        // CTA-uniform shapes (per-element branching on split / beta made ptxas reload alpha from constant memory
+        // before every store)
+        const double alpha = p.alpha;
+        double* cp = p.C + c_off;
+        if (c_vec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<double2*>(cp + (long long)(i * 8) * p.ldc + j * 8) =
+                        make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+        } else if (interior) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cp[(long long)(i * 8) * p.ldc + j * 8] = alpha * acc[i][j][0];
+                    cp[(long long)(i * 8) * p.ldc + j * 8 + 1] = alpha * acc[i][j][1];
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long gm = m0 + wm * 64 + i * 8 + fr;
+                if (gm >= p.M) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long gn = n0 + wn * 32 + j * 8 + 2 * fc;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (gn + e < p.N) p.C[gm * p.ldc + gn + e] = alpha * acc[i][j][e];
+                }
+            }
+        }
+        return;
+    }
     const bool split = p.part != nullptr;
     double* out = split ? p.part + (size_t)blockIdx.z * p.M * p.N : p.C;
     const long long ldo = split ? p.N : p.ldc;
@@ -468,7 +559,7 @@ static int choose_splits(long long M, long long N, long long K) {
 }
 
 template <int TA, int TB>
-static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, bool vec16, cudaStream_t st) {
+static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, int vec16, cudaStream_t st) {
     const int splits = choose_splits(p.M, p.N, p.K);
     const long long ktiles = (p.K + GM_BK - 1) / GM_BK;
     p.ktiles_per_split = (int)((ktiles + splits - 1) / splits);
@@ -482,13 +573,21 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, bool vec16, cud
     dim3 grid((unsigned)((p.N + GM_BN - 1) / GM_BN), (unsigned)((p.M + GM_BM - 1) / GM_BM), (unsigned)zs);
     const size_t smem = (size_t)2 * GM_STAGES * GM_TILE * sizeof(double);
     cudaError_t e;
-    if (vec16) {
-        e = cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) { gemm_f64_kernel<TA, TB, true><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); note_launch(); }
+    // the update form (beta != 0, no split-K) of the plain product has its own instantiation
+    const bool cacc = (TA == 0 && TB == 0) && zs == 1 && p.beta != 0.0 && p.alpha != 0.0;
+#define PLA_GEMM_LAUNCH(V, C)                                                                                             \
+    do {                                                                                                                  \
+        e = cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, V, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e == cudaSuccess) { gemm_f64_kernel<TA, TB, V, C><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); note_launch(); } \
+    } while (0)
+    if (cacc) {
+        if constexpr (TA == 0 && TB == 0) {
+            if (vec16 == 1) PLA_GEMM_LAUNCH(1, true); else if (vec16 == 2) PLA_GEMM_LAUNCH(2, true); else PLA_GEMM_LAUNCH(0, true);
+        }
     } else {
-        e = cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) { gemm_f64_kernel<TA, TB, false><<<grid, GM_THREADS, smem, st>>>(p); e = cudaGetLastError(); note_launch(); }
+        if (vec16 == 1) PLA_GEMM_LAUNCH(1, false); else if (vec16 == 2) PLA_GEMM_LAUNCH(2, false); else PLA_GEMM_LAUNCH(0, false);
     }
+#undef PLA_GEMM_LAUNCH
     if (e != cudaSuccess) { set_error("gemm: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     if (zs > 1) {
         long long total = p.M * p.N;
@@ -607,10 +706,10 @@ extern "C" int pla_gemm_f64(int transa, int transb, int64_t M, int64_t N, int64_
     GemmParams p;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
     p.alpha = alpha; p.beta = beta; p.seed = 0; p.col_offset = 0; p.part = nullptr; p.Nb = N; p.xcol = nullptr;
-    // 16-byte copies need even leading dimensions AND even extents along the contiguous axis
-    const bool a_ok = aligned16(A, lda) && ((transa ? M : K) % 2 == 0);
-    const bool b_ok = aligned16(B, ldb) && ((transb ? K : N) % 2 == 0);
-    const bool vec16 = a_ok && b_ok;
+    // 16-byte copies need 16-byte aligned rows (even leading dimension); an odd extent along the contiguous axis
+    // ends in a half-filled slot (cp.async src-size 8), so the d x (n + 1) sketch with its even pitch qualifies
+    const bool even = ((transa ? M : K) % 2 == 0) && ((transb ? K : N) % 2 == 0);
+    const int vec16 = (aligned16(A, lda) && aligned16(B, ldb)) ? (even ? 1 : 2) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (!transa && !transb) return launch_gemm<0, 0>(p, ws, ws_bytes, vec16, st);
     if (transa && !transb) return launch_gemm<1, 0>(p, ws, ws_bytes, vec16, st);

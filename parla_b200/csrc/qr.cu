@@ -1105,8 +1105,8 @@ struct QrWs {
     size_t ll_bytes;
     double* cpart;           // [QB_MAXG][QB_NV] reduce-scatter partials
     long long* prof;         // [QB_MAXG][QB_NPROF] debug cycle counters
-    double* Wbig;            // 128 x N
-    double* W2big;           // 128 x N
+    double* Wbig;            // 128 x (N + 1)
+    double* W2big;           // 128 x (N + 1)
     void* gemm_ws; size_t gemm_ws_bytes;
 };
 
@@ -1131,8 +1131,8 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
     const size_t o_ll = take(ll_lines * sizeof(LLLine));
     const size_t o_cp = take((size_t)QB_MAXG * QB_NV * 8);
     const size_t o_pf = take((size_t)QB_MAXG * QB_NPROF * 8);
-    const size_t o_wb = take((size_t)QR_NBO * (size_t)N * 8);
-    const size_t o_w2 = take((size_t)QR_NBO * (size_t)N * 8);
+    const size_t o_wb = take((size_t)QR_NBO * (size_t)(N + 1) * 8);        // even pitch: nc + (nc & 1) <= N + 1
+    const size_t o_w2 = take((size_t)QR_NBO * (size_t)(N + 1) * 8);
     // split-K partials of the block-reflector GEMMs: at most 64 splits of a 128 x nc tile row (nc <= N)
     const size_t gws = (size_t)64 * QR_NBO * (size_t)(N > QR_NBO ? N : QR_NBO) * 8;
     const size_t o_gw = take(gws + 256);
@@ -1312,15 +1312,16 @@ static int apply_block_reflector(long long M, long long J0, int JB, const double
     if (nc <= 0) return 0;
     const long long rows = M - J0;
     double* Crows = C + J0 * ldc;
-    int rc = pla_gemm_f64(1, 0, QR_NBO, nc, rows, 1.0, w.Vx, QR_NBO, Crows, ldc, 0.0, w.Wbig, nc, w.gemm_ws,
+    const long long ldw = nc + (nc & 1);     // 16-byte aligned rows: the second product reads W2 with vector copies
+    int rc = pla_gemm_f64(1, 0, QR_NBO, nc, rows, 1.0, w.Vx, QR_NBO, Crows, ldc, 0.0, w.Wbig, ldw, w.gemm_ws,
                           w.gemm_ws_bytes, st);                                   // W = Vx^T C
     if (rc) return rc;
     const size_t smem = ((size_t)QR_NBO * QR_NBO + (size_t)QR_NBO * QW_THREADS + QR_NBO) * sizeof(double);
     PLA_CUDA(cudaFuncSetAttribute(qr_w2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     qr_w2_kernel<<<(unsigned)((nc + QW_THREADS - 1) / QW_THREADS), QW_THREADS, smem, st>>>(
-        w.Gbig, tau_blk, JB, w.Wbig, nc, nc, w.W2big, nc, t_transpose);           // W2 = op(T) W
+        w.Gbig, tau_blk, JB, w.Wbig, ldw, nc, w.W2big, ldw, t_transpose);         // W2 = op(T) W
     PLA_LAUNCH_CHECK();
-    return pla_gemm_f64(0, 0, rows, nc, QR_NBO, -1.0, w.Vx, QR_NBO, w.W2big, nc, 1.0, Crows, ldc, w.gemm_ws,
+    return pla_gemm_f64(0, 0, rows, nc, QR_NBO, -1.0, w.Vx, QR_NBO, w.W2big, ldw, 1.0, Crows, ldc, w.gemm_ws,
                         w.gemm_ws_bytes, st);                                     // C -= Vx W2
 }
 

@@ -192,6 +192,28 @@ def test_gemm_strided_views(K):
     assert float(out[:, :2].abs().sum()) == 0 and float(out[:, 35:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K_", [(131, 257, 77), (128, 1921, 301), (515, 129, 128)])
+def test_gemm_odd_extents_on_an_even_pitch(K, ta, tb, M, N, K_):
+    """Odd extents in buffers whose rows are 16-byte aligned (the d x (n + 1) sketch inside the QR) take the
+    16-byte copy path with a half-filled last slot; the pad column holds NaN, so touching it poisons the result."""
+    rng = np.random.default_rng(M + N + K_ + ta + 2 * tb)
+
+    def padded(x):
+        r, c = x.shape
+        buf = torch.full((r, c + (c & 1)), float("nan"), dtype=torch.float64, device="cuda")
+        buf[:, :c] = dev(x)
+        return buf[:, :c]
+
+    A = rng.standard_normal((K_, M) if ta else (M, K_))
+    B = rng.standard_normal((N, K_) if tb else (K_, N))
+    C0 = rng.standard_normal((M, N))
+    ref = 0.5 * (A.T if ta else A) @ (B.T if tb else B) - C0
+    C = padded(C0)
+    K.gemm(padded(A), padded(B), transa=bool(ta), transb=bool(tb), alpha=0.5, beta=-1.0, out=C)
+    assert rel(C, ref) < 1e-13
+
+
 # ------------------------------------------------------------------ Philox / Gaussian sketch
 def test_philox_fill_matches_oracle_definition(K):
     S = K.philox_normal_fill(37, 1001, seed=2024, scale=0.5, row_offset=3, col_offset=6).cpu().numpy()
