@@ -30,6 +30,7 @@ struct GemmParams {
     const double* xcol;               // optional extra logical column of B (length K)
     double alpha, beta;
     int ktiles_per_split;
+    int ctas_in_flight;               // CACC kernels: tiles computed concurrently (one per SM); 0 = no next-tile prefetch
     // Gaussian-operator mode (A operand generated): S[r][kglobal]
     uint64_t seed; long long col_offset;
 };
@@ -246,6 +247,21 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_f64_kernel(const GemmParam
     for (int s = 0; s < GM_STAGES - 1; ++s) {
         if (s < nkt) { issue_a(s, -1); issue_b(s); }
         cp_async_commit();
+    }
+    if (CACC) {
+        // The C tile of the CTA that will follow on this SM (linear tile id + #CTAs in flight = one per SM) is pulled
+        // into L2 while this tile computes, so its 128 KB of loads do not start a wave with a DRAM round trip.
+        const long long nxt = (long long)blockIdx.y * gridDim.x + blockIdx.x + p.ctas_in_flight;
+        const long long ny = nxt / gridDim.x, nx = nxt - ny * gridDim.x;
+        if (p.ctas_in_flight > 0 && ny < gridDim.y) {
+            const long long pm0 = ny * GM_BM, pn0 = nx * GM_BN;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                    // 128 rows x 8 lines of 128 bytes
+                const int line = tid + GM_THREADS * i;
+                const long long r = pm0 + (line >> 3), cc = pn0 + 16 * (line & 7);
+                if (r < p.M && cc < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.C + r * p.ldc + cc));
+            }
+        }
     }
     if (CACC) {                                          // scale once the operand copies are on their way
         const double f = p.beta / p.alpha;
@@ -543,17 +559,23 @@ static int choose_splits(long long M, long long N, long long K) {
     const long long ktiles = (K + GM_BK - 1) / GM_BK;
     const long long sms = num_sms();
     if (tiles >= 4 * sms || ktiles < 16) return 1;
-    // pick the split count whose CTA count fills whole waves best: >= 32 k-tiles per split, or >= 8 when the output
-    // has fewer tiles than SMs (the 128 x nc products inside the QR: a handful of tiles with K = thousands of rows)
-    long long smax = ktiles / (tiles < sms ? 8 : 32);
+    // Few output tiles, long K (Gram matrices, the 128 x nc products inside the QR): split K over gridDim.z.  The
+    // split count minimises a small cost model in microseconds -- waves x (k-tiles per CTA x 2.4 + 6 fixed) for the
+    // product (one CTA per SM; 2.4 us per 128 x 128 x 16 step at the DMMA rate) plus, when split, the reduce kernel
+    // (6 us + the partial tiles written and read back at ~4 TB/s).  Filling the last wave exactly is not worth four
+    // times as many partials: 37 splits of 128 x 1921 x 8192 measured 203 us where the model's 9 splits take ~155.
+    long long smax = ktiles / 8;
     if (smax > 64) smax = 64;
     int best = 1;
-    double best_eff = (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);
-    for (long long sp = 2; sp <= smax; ++sp) {
-        const long long ctas = tiles * sp;
-        const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = (int)sp; }
-        if (ctas >= 8 * sms) break;
+    double best_t = 0.0;
+    for (long long sp = 1; sp <= smax || sp == 1; ++sp) {
+        const long long kps = (ktiles + sp - 1) / sp;
+        const long long zs = (ktiles + kps - 1) / kps;           // splits actually launched
+        if (zs != sp && sp > 1) continue;
+        const long long waves = (tiles * zs + sms - 1) / sms;
+        double t = (double)waves * ((double)kps * 2.4 + 6.0);
+        if (zs > 1) t += 6.0 + (double)zs * (double)M * (double)N * 16.0 / 4.0e6;
+        if (sp == 1 || t < 0.97 * best_t) { best_t = t; best = (int)zs; }     // more partials only for a real gain
     }
     return best;
 }
@@ -575,6 +597,8 @@ static int launch_gemm(GemmParams& p, void* ws, size_t ws_bytes, int vec16, cuda
     cudaError_t e;
     // the update form (beta != 0, no split-K) of the plain product has its own instantiation
     const bool cacc = (TA == 0 && TB == 0) && zs == 1 && p.beta != 0.0 && p.alpha != 0.0;
+    static const bool pf = [] { const char* e = getenv("PLA_GEMM_PREFETCH"); return !(e && e[0] == '0'); }();
+    p.ctas_in_flight = pf ? num_sms() : 0;
 #define PLA_GEMM_LAUNCH(V, C)                                                                                             \
     do {                                                                                                                  \
         e = cudaFuncSetAttribute(gemm_f64_kernel<TA, TB, V, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
@@ -706,6 +730,7 @@ extern "C" int pla_gemm_f64(int transa, int transb, int64_t M, int64_t N, int64_
     GemmParams p;
     p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
     p.alpha = alpha; p.beta = beta; p.seed = 0; p.col_offset = 0; p.part = nullptr; p.Nb = N; p.xcol = nullptr;
+    p.ctas_in_flight = 0;
     // 16-byte copies need 16-byte aligned rows (even leading dimension); an odd extent along the contiguous axis
     // ends in a half-filled slot (cp.async src-size 8), so the d x (n + 1) sketch with its even pitch qualifies
     const bool even = ((transa ? M : K) % 2 == 0) && ((transb ? K : N) % 2 == 0);
@@ -746,7 +771,7 @@ extern "C" int pla_sketch_gauss_f64(const double* A, int64_t m, int64_t n, int64
     p.A = nullptr; p.lda = 0; p.B = A; p.ldb = lda; p.C = out; p.ldc = ldo; p.M = d; p.K = m;
     p.N = separate_b ? n : ncols;
     p.Nb = n; p.xcol = separate_b ? nullptr : bvec;
-    p.alpha = scale; p.beta = beta; p.seed = seed; p.col_offset = col_offset; p.part = nullptr;
+    p.alpha = scale; p.beta = beta; p.seed = seed; p.col_offset = col_offset; p.part = nullptr; p.ctas_in_flight = 0;
     const bool vec16 = aligned16(A, lda) && (n % 2 == 0);
     int rc = launch_gauss(p, ws, ws_bytes, vec16, st);
     if (rc != 0 || !separate_b) return rc;
