@@ -55,6 +55,31 @@ int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_t lda, cons
                         const double* g, const double* sc_dev, double sa, double su, double* zss, int flags,
                         const int* istop_dev, void* ws, size_t ws_bytes, void* stream);
 
+/* Row-sharded A (one process per GPU of a node): the same pass, with the sum over the ranks of
+ * zss = [z | |u|^2] (the reference has no counterpart: its `np.dot(A.T, u)` at preconditioning.py:34 sees all rows)
+ * fused into the reduce kernel as a one-shot all-reduce over NVLink peer memory instead of a separate NCCL call:
+ * the thread that finishes column c stores {value, epoch} lines into every rank's exchange buffer and adds the
+ * `world` lines of its own buffer in rank order (bit-identical on every rank).
+ *   peer_recv : HOST array of `world` device pointers, peer_recv[r] = rank r's exchange buffer (pla_peer_alloc on
+ *               rank r, mapped here with pla_peer_import; peer_recv[rank] is the local allocation), each of
+ *               pla_peer_exchange_bytes(world, slot_lines) bytes, slot_lines >= n + 1
+ *   epoch     : call counter, identical on all ranks, starting at 1 and incremented by every call that uses the
+ *               buffers (flag 0 = never written).  All ranks must make the same sequence of calls.
+ * 1 <= world <= 8 (world = 1 exchanges with itself).  A rank whose peers do not answer within 30 s gets NaN in
+ * zss instead of hanging the GPU.                                                                             */
+int pla_stream_pass_peer_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
+                             const double* g, const double* sc_dev, double sa, double su, double* zss, int flags,
+                             const int* istop_dev, void* ws, size_t ws_bytes, void* const* peer_recv, int rank,
+                             int world, int64_t slot_lines, uint32_t epoch, void* stream);
+size_t pla_peer_exchange_bytes(int world, int64_t slot_lines);
+/* Exchange buffers: a zero-filled cudaMalloc block (not torch's allocator: CUDA IPC exports whole allocations),
+ * its 64-byte CUDA IPC handle, and the mapping of another rank's handle into this process.                   */
+int pla_peer_alloc(size_t bytes, void** dev_ptr);
+int pla_peer_free(void* dev_ptr);
+int pla_peer_export(const void* dev_ptr, unsigned char* handle64);
+int pla_peer_import(const unsigned char* handle64, void** peer_ptr);
+int pla_peer_close(void* peer_ptr);
+
 /* ---------------------------------------------------------------- K3b: triangular solve, one rhs
  * Replaces scipy.linalg.solve_triangular(R, x, trans, lower=False) at
  *   parla/comps/preconditioning.py:28,37,40,41 and parla/drivers/least_squares.py:316,363.

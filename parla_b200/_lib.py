@@ -23,6 +23,14 @@ SIGNATURES = {
     "pla_stream_pass_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "pla_stream_pass_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_int,
                                     c_vp, c_vp, c_sz, c_vp]),
+    "pla_stream_pass_peer_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_int,
+                                         c_vp, c_vp, c_sz, c_vp, c_int, c_int, c_i64, C.c_uint32, c_vp]),
+    "pla_peer_exchange_bytes": (c_sz, [c_int, c_i64]),
+    "pla_peer_alloc": (c_int, [c_sz, c_vp]),
+    "pla_peer_free": (c_int, [c_vp]),
+    "pla_peer_export": (c_int, [c_vp, c_vp]),
+    "pla_peer_import": (c_int, [c_vp, c_vp]),
+    "pla_peer_close": (c_int, [c_vp]),
     "pla_trsv_upper_f64": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "pla_trtri_diag_f64": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "pla_trtri_merge_f64": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),

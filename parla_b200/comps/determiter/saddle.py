@@ -8,7 +8,7 @@ SURVEY.md 8(f).
 import torch
 
 from ... import kernels as K
-from ...parallel import allreduce_, unwrap
+from ...parallel import allreduce_, peer_comm, unwrap
 from .lsqr import lsqr, lsqr_adjoint
 from .pcg import pcg
 from ..preconditioning import a_lift_precond
@@ -46,20 +46,21 @@ class GramOperator:
         self.u = torch.empty(self.m_local, dtype=F64, device=self.A.device)     # A vec (scratch, write-only)
         self.zss = torch.empty(self.n + 1, dtype=F64, device=self.A.device)
         self.passes = 0
+        self.comm = peer_comm(self.group, self.A.device) if self.A.is_cuda else None   # see PrecondOperator
+
+    def _pass(self, **kw):
+        zss = K.stream_pass(self.A, comm=self.comm, **kw)
+        self.passes += 1
+        if self.comm is None:
+            allreduce_(zss, self.group)
+        return zss
 
     def __call__(self, vec, istop=None):
-        K.stream_pass(self.A, w=vec, u=self.u, sa=1.0, su=0.0, zss=self.zss, flags=K.PASS_DOT | K.PASS_AXPY,
-                      istop=istop)
-        self.passes += 1
-        allreduce_(self.zss, self.group)
-        return self.zss
+        return self._pass(w=vec, u=self.u, sa=1.0, su=0.0, zss=self.zss, flags=K.PASS_DOT | K.PASS_AXPY, istop=istop)
 
     def rmatvec(self, y):
         """A^T y summed over row shards (fresh tensor)."""
-        zss = K.stream_pass(self.A, u=y, flags=K.PASS_AXPY)
-        self.passes += 1
-        allreduce_(zss, self.group)
-        return zss[:self.n].clone()
+        return self._pass(u=y, flags=K.PASS_AXPY)[:self.n].clone()
 
     def residual(self, x, b):
         """b - A x on this rank's rows."""

@@ -13,7 +13,7 @@ import os
 import torch
 
 from .. import kernels as K
-from ..parallel import allreduce_, unwrap
+from ..parallel import allreduce_, peer_comm, unwrap
 
 F64 = torch.float64
 
@@ -38,6 +38,17 @@ class PrecondOperator:
         self.passes = 0
         self.atb = None          # cache of A^T b when a pass happened to produce it
         self._zt = None          # scratch of precond_t (rank + 1 doubles), allocated once
+        # row-sharded A on the GPUs of one node: the sum of [z | |u|^2] over the ranks rides inside the pass's reduce
+        # kernel (NVLink peer memory); otherwise (None) an NCCL all-reduce follows the pass
+        self.comm = peer_comm(self.group, self.A.device) if self.A.is_cuda else None
+
+    def _pass(self, **kw):
+        """One streaming pass over this rank's rows; ``zss`` comes back summed over the ranks."""
+        zss = K.stream_pass(self.A, comm=self.comm, **kw)
+        self.passes += 1
+        if self.comm is None:
+            allreduce_(zss, self.group)
+        return zss
 
     # ---- M and M^T on n-vectors (preconditioning.py:40-41 / :56-57)
     def precond(self, z, out=None, istop=None):
@@ -64,9 +75,7 @@ class PrecondOperator:
         """u~ <- sa * A_pc z + su * u~ (top part in ``u``, ridge part in ``ub``);
         t <- M^T [A; sd I]^T u~ ;  zss[n] <- |u~|^2.   (preconditioning.py:26-38 forward + adjoint)"""
         self.precond(z, out=xw, istop=istop)
-        K.stream_pass(self.A, w=xw, u=u, sc=sc, sa=sa, su=su, zss=zss, flags=K.PASS_DOT | K.PASS_AXPY, istop=istop)
-        self.passes += 1
-        allreduce_(zss, self.group)
+        self._pass(w=xw, u=u, sc=sc, sa=sa, su=su, zss=zss, flags=K.PASS_DOT | K.PASS_AXPY, istop=istop)
         if self.delta > 0:
             K.lsqr_ridge(self.sd, xw, ub, zss, sc=sc, sa=sa, su=su, istop=istop)
         self.precond_t(zss[:self.n], out=t, istop=istop)
@@ -74,9 +83,7 @@ class PrecondOperator:
 
     def adjoint_pass(self, u, ub, zss, t):
         """t <- M^T (A^T u + sd * ub), zss[n] <- |[u; ub]|^2 (no forward product)."""
-        K.stream_pass(self.A, u=u, zss=zss, flags=K.PASS_AXPY)
-        self.passes += 1
-        allreduce_(zss, self.group)
+        self._pass(u=u, zss=zss, flags=K.PASS_AXPY)
         if self.delta > 0 and ub is not None:
             K.lsqr_ridge(self.sd, None, ub, zss, sa=0.0, su=1.0)
         self.precond_t(zss[:self.n], out=t)
@@ -84,9 +91,7 @@ class PrecondOperator:
 
     def rmatvec_plain(self, y):
         """A^T y (no preconditioner, no ridge rows), summed over row shards."""
-        zss = K.stream_pass(self.A, u=y, flags=K.PASS_AXPY)
-        self.passes += 1
-        allreduce_(zss, self.group)
+        zss = self._pass(u=y, flags=K.PASS_AXPY)
         return zss[:self.n].clone()
 
     def matvec_plain(self, x):
@@ -99,9 +104,7 @@ class PrecondOperator:
     def residual_and_atb(self, x, b):
         """y = b - A x and A^T b in one pass (saddle.py:199 and least_squares.py:361 fused)."""
         y = b.clone()
-        zss = K.stream_pass(self.A, w=x, u=y, g=b, sa=-1.0, su=1.0, flags=K.PASS_DOT | K.PASS_AXPY | K.PASS_AXPY_G)
-        self.passes += 1
-        allreduce_(zss, self.group)
+        zss = self._pass(w=x, u=y, g=b, sa=-1.0, su=1.0, flags=K.PASS_DOT | K.PASS_AXPY | K.PASS_AXPY_G)
         self.atb = zss[:self.n].clone()
         return y
 

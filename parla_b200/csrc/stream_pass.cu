@@ -8,6 +8,7 @@
 // the TMA engine (cp.async.bulk + mbarrier ring) and consumed twice on chip (row dots, then the
 // transposed accumulation), so HBM traffic per LSQR iteration is m*n*8 bytes instead of 2*m*n*8.
 // Reductions are fixed-order (thread -> warp tree -> warp list -> CTA list): run-to-run deterministic.
+#include <cstring>
 #include "common.cuh"
 #include "../../include/parla_b200.h"
 
@@ -273,17 +274,56 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
 // warp results are added in warp order.  (One thread per column walking all ~600 partials serially cost 30-40 us,
 // several times the streaming pass itself on a 2^16 x 500 matrix.)
 constexpr int SPR_COLS = 32, SPR_WARPS = 8;
+
+// ---- cross-GPU sum fused into the reduce: one-shot all-reduce over NVLink peer memory ---------------------------
+// When A is row-sharded over the GPUs of a node, [z | |u|^2] must be summed over the ranks before the LSQR step
+// (collective (2): n + 1 doubles per iteration, latency-critical).  Instead of a separate NCCL all-reduce,
+// the thread that finishes column c PUSHES its total into slot [epoch parity][my rank][c] of every rank's exchange
+// buffer (plain stores into peer memory mapped with CUDA IPC) and then polls the `world` slots of its OWN buffer,
+// adding them in rank order -- every rank obtains the same bits.  A slot is a 16-byte line {lo, flag, hi, flag}
+// (the NCCL "LL" layout: each 8-byte half carries the epoch, so a line is valid exactly when both flags match and no
+// fence or barrier is needed); flag = epoch of the call, counted identically on every rank.  Two parities suffice:
+// a rank can only reach call e + 2 after it has received every peer's data of call e + 1, which a peer sends after
+// its kernel of call e has finished reading.  A poll gives up after 30 s (a missing peer) and returns NaN.
+constexpr int SP_MAX_PEERS = 8;
+struct PeerLine { uint32_t lo, f0, hi, f1; };
+struct PeerExchange {
+    PeerLine* recv[SP_MAX_PEERS];       // exchange buffer of every rank (recv[rank] is local memory)
+    int rank, world;                    // world == 0: no exchange (world == 1 exchanges with itself: test hook)
+    long long stride;                   // lines per (parity, source rank) slot, >= n + 1
+    uint32_t epoch;
+};
+__device__ __forceinline__ void peer_store(PeerLine* line, double v, uint32_t flag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"((uint32_t)b), "r"(flag),
+                 "r"((uint32_t)(b >> 32)), "r"(flag)
+                 : "memory");
+}
+__device__ __forceinline__ bool peer_try_load(const PeerLine* line, uint32_t flag, double& v) {
+    uint32_t a, f0, c, f1;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(f0), "=r"(c), "=r"(f1) : "l"(line) : "memory");
+    if (f0 != flag || f1 != flag) return false;
+    v = __longlong_as_double((long long)(((unsigned long long)c << 32) | a));
+    return true;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(SPR_COLS * SPR_WARPS) stream_pass_reduce_kernel(const double* __restrict__ zpart,
                                                                                    const double* __restrict__ sspart,
                                                                                    int nblk, long long n,
                                                                                    double* __restrict__ zss, int do_axpy,
-                                                                                   const int* istop) {
+                                                                                   const int* istop, const PeerExchange px) {
     if (istop != nullptr && *istop != 0) return;
     __shared__ double acc_s[SPR_WARPS][SPR_COLS + 1];
     const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long long c = (long long)blockIdx.x * SPR_COLS + cl;      // column n is the |u|^2 slot
+    const bool live = c < n ? do_axpy != 0 : c == n;
     double acc = 0.0;
-    if (c < n ? do_axpy != 0 : c == n) {
+    if (live) {
         const double* src = c < n ? zpart + c : sspart;
         const long long stride = c < n ? n : 1;
         for (int b0 = grp; b0 < nblk; b0 += SPR_WARPS * 8) {
@@ -302,6 +342,32 @@ __global__ void __launch_bounds__(SPR_COLS * SPR_WARPS) stream_pass_reduce_kerne
         double tot = 0.0;
 #pragma unroll
         for (int g2 = 0; g2 < SPR_WARPS; ++g2) tot += acc_s[g2][cl];
+        if (px.world > 0 && live) {
+            const size_t par = (size_t)(px.epoch & 1u) * px.world;
+            const size_t mine = (par + px.rank) * px.stride + (size_t)c;
+#pragma unroll
+            for (int r = 0; r < SP_MAX_PEERS; ++r)
+                if (r < px.world) peer_store(px.recv[r] + mine, tot, px.epoch);
+            const PeerLine* in = px.recv[px.rank] + par * px.stride + (size_t)c;
+            double v[SP_MAX_PEERS];
+            unsigned pending = (1u << px.world) - 1u;
+            const unsigned long long t0 = global_timer_ns();
+            while (pending != 0) {
+#pragma unroll
+                for (int r = 0; r < SP_MAX_PEERS; ++r)
+                    if (((pending >> r) & 1u) && peer_try_load(in + (size_t)r * px.stride, px.epoch, v[r])) pending &= ~(1u << r);
+                if (pending != 0 && global_timer_ns() - t0 > 30000000000ull) {
+#pragma unroll
+                    for (int r = 0; r < SP_MAX_PEERS; ++r)
+                        if ((pending >> r) & 1u) v[r] = __longlong_as_double(0x7ff8000000000000ll);
+                    pending = 0;
+                }
+            }
+            tot = 0.0;
+#pragma unroll
+            for (int r = 0; r < SP_MAX_PEERS; ++r)
+                if (r < px.world) tot += v[r];
+        }
         zss[c] = tot;
     }
 }
@@ -350,9 +416,9 @@ extern "C" size_t pla_stream_pass_workspace_bytes(int64_t m, int64_t n) {
     return (size_t)num_sms() * SP_MAX_GROUPS * (size_t)(n + 1) * sizeof(double) + 256;
 }
 
-extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
-                                   const double* g, const double* sc_dev, double sa, double su, double* zss,
-                                   int flags, const int* istop_dev, void* ws, size_t ws_bytes, void* stream) {
+static int stream_pass_impl(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
+                            const double* g, const double* sc_dev, double sa, double su, double* zss,
+                            int flags, const int* istop_dev, void* ws, size_t ws_bytes, void* stream, const PeerExchange& px) {
     PLA_CHECK_ARG(A != nullptr, 1, "A is null");
     PLA_CHECK_ARG(m >= 1, 2, "m < 1");
     PLA_CHECK_ARG(n >= 1 && n <= PLA_PASS_MAX_N, 3, "n out of range for the streaming pass (1..8192)");
@@ -409,7 +475,36 @@ extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_
     if (e != cudaSuccess) { set_error("pla_stream_pass_f64: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     const int rb = (int)((n + 1 + SPR_COLS - 1) / SPR_COLS);
     stream_pass_reduce_kernel<<<rb, SPR_COLS * SPR_WARPS, 0, st>>>(p.zpart, p.sspart, nparts, n, zss, do_axpy ? 1 : 0,
-                                                                  istop_dev);
+                                                                  istop_dev, px);
     PLA_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
+                                   const double* g, const double* sc_dev, double sa, double su, double* zss,
+                                   int flags, const int* istop_dev, void* ws, size_t ws_bytes, void* stream) {
+    PeerExchange px;
+    memset(&px, 0, sizeof(px));
+    return stream_pass_impl(A, m, n, lda, w, u, g, sc_dev, sa, su, zss, flags, istop_dev, ws, ws_bytes, stream, px);
+}
+
+extern "C" int pla_stream_pass_peer_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
+                                        const double* g, const double* sc_dev, double sa, double su, double* zss,
+                                        int flags, const int* istop_dev, void* ws, size_t ws_bytes,
+                                        void* const* peer_recv, int rank, int world, int64_t slot_lines, uint32_t epoch,
+                                        void* stream) {
+    PLA_CHECK_ARG(world >= 1 && world <= SP_MAX_PEERS && rank >= 0 && rank < world, 18, "need 0 <= rank < world <= 8");
+    PLA_CHECK_ARG(peer_recv != nullptr && slot_lines >= n + 1 && epoch != 0, 17, "bad exchange buffers / slot size / epoch");
+    PeerExchange px;
+    memset(&px, 0, sizeof(px));
+    for (int r = 0; r < world; ++r) {
+        PLA_CHECK_ARG(peer_recv[r] != nullptr, 17, "null peer buffer");
+        px.recv[r] = (PeerLine*)peer_recv[r];
+    }
+    px.rank = rank; px.world = world; px.stride = slot_lines; px.epoch = epoch;
+    return stream_pass_impl(A, m, n, lda, w, u, g, sc_dev, sa, su, zss, flags, istop_dev, ws, ws_bytes, stream, px);
+}
+
+extern "C" size_t pla_peer_exchange_bytes(int world, int64_t slot_lines) {
+    return (size_t)2 * (size_t)world * (size_t)slot_lines * sizeof(PeerLine);
 }

@@ -96,19 +96,24 @@ def num_sms():
 
 
 # ---------------------------------------------------------------------------------------- K4
-def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None, flags=PASS_DOT, istop=None):
+def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None, flags=PASS_DOT, istop=None, comm=None):
     """One streaming read of A:  u <- sa*(A w) + su*u ;  z = A^T q ;  zss = [z, |u|^2].
 
     Returns zss (n+1 doubles).  See pla_stream_pass_f64.  Matrices wider than PASS_MAX_N columns go through
     column blocks (two reads of A when both products are requested: z needs the complete u).
+    With ``comm`` (a parallel.PeerComm: A is this rank's row block) zss comes back summed over the ranks -- inside
+    the reduce kernel, over NVLink peer memory (pla_stream_pass_peer_f64); the column-blocked path all-reduces.
     """
     lib = _lib.load()
     A, lda = _rowmajor(A, "A")
     m, n = A.shape
     if zss is None:
         zss = torch.empty(n + 1, dtype=F64, device=A.device)
-    if n > PASS_MAX_N or (n % 2 == 1 and n > PASS_MAX_N // 2):
-        return _stream_pass_wide(A, w, u, g, sc, sa, su, zss, flags, istop)
+    if n > PASS_MAX_N or (n % 2 == 1 and n > PASS_MAX_N // 2) or (comm is not None and n + 1 > comm.slot_lines):
+        zss = _stream_pass_wide(A, w, u, g, sc, sa, su, zss, flags, istop)
+        if comm is not None and comm.world > 1:
+            torch.distributed.all_reduce(zss, group=comm.group)
+        return zss
     nb = lib.pla_stream_pass_workspace_bytes(m, n)
     ws = Workspace.get(A.device, nb, "pass")
     rec = PASS_TIMINGS
@@ -117,8 +122,13 @@ def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None,
     if rec is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = lib.pla_stream_pass_f64(A.data_ptr(), m, n, lda, _p(w), _p(u), _p(g), _p(sc), float(sa), float(su),
-                                 zss.data_ptr(), int(flags), _p(istop), ws.data_ptr(), ws.numel(), _stream())
+    if comm is None:
+        rc = lib.pla_stream_pass_f64(A.data_ptr(), m, n, lda, _p(w), _p(u), _p(g), _p(sc), float(sa), float(su),
+                                     zss.data_ptr(), int(flags), _p(istop), ws.data_ptr(), ws.numel(), _stream())
+    else:
+        rc = lib.pla_stream_pass_peer_f64(A.data_ptr(), m, n, lda, _p(w), _p(u), _p(g), _p(sc), float(sa), float(su),
+                                          zss.data_ptr(), int(flags), _p(istop), ws.data_ptr(), ws.numel(), comm.ptrs,
+                                          comm.rank, comm.world, comm.slot_lines, comm.next_epoch(), _stream())
     _lib.check(rc, "pla_stream_pass_f64")
     if rec is not None:
         e1.record()

@@ -29,6 +29,27 @@ def main():
         if rank == 0:
             print(f"{'OK  ' if good else 'FAIL'} {name:58s} {err:.3e} (tol {tol:.0e})", flush=True)
 
+    # ---------------- fused reduce + cross-GPU sum of the streaming pass (NVLink peer memory) vs pass + NCCL all-reduce
+    from parla_b200 import kernels as K
+    from parla_b200.parallel import peer_comm
+    comm = peer_comm(dist.group.WORLD, dev)
+    if rank == 0:
+        print("peer exchange:", "ON (pla_stream_pass_peer_f64)" if comm is not None else "OFF (NCCL all-reduce)", flush=True)
+    if comm is not None:
+        for trial, (mm, nn) in enumerate([(5000, 500), (4096, 2048), (3000, 64), (2048, 4096), (3000, 64)]):
+            g = torch.Generator(device=dev).manual_seed(50 * trial + rank)
+            At = torch.randn(mm, nn, dtype=torch.float64, device=dev, generator=g)
+            wt = torch.randn(nn, dtype=torch.float64, device=dev, generator=g)
+            u1, u2 = torch.zeros(mm, dtype=torch.float64, device=dev), torch.zeros(mm, dtype=torch.float64, device=dev)
+            z_ref = K.stream_pass(At, w=wt, u=u1, flags=K.PASS_DOT | K.PASS_AXPY)
+            dist.all_reduce(z_ref)
+            z_f = K.stream_pass(At, w=wt, u=u2, flags=K.PASS_DOT | K.PASS_AXPY, comm=comm)
+            report(f"fused pass + peer sum {mm}x{nn} vs pass + NCCL all-reduce",
+                   float(torch.linalg.vector_norm(z_f - z_ref) / torch.linalg.vector_norm(z_ref)), 1e-14)
+            zs = [torch.empty_like(z_f) for _ in range(world)]
+            dist.all_gather(zs, z_f)
+            report(f"fused pass + peer sum {mm}x{nn} identical on every rank", max(float((z - zs[0]).abs().max()) for z in zs), 0.0)
+
     # ---------------- least squares: same global (A, b) on every rank, rows split evenly
     rng = np.random.default_rng(0)
     m, n = 4096 * world, 200
@@ -50,7 +71,7 @@ def main():
     report("SPO[replayed scipy SJLT] sharded vs oracle", float(np.linalg.norm(xs.cpu().numpy() - x_ref) / np.linalg.norm(x_ref)), 1e-10)
 
     # ---------------- column-distributed QR of the replicated sketch (engages for n >= 2 * 128 * world)
-    from parla_b200 import kernels as K, distla
+    from parla_b200 import distla
     nq = 256 * world + 130
     g = torch.Generator(device=dev).manual_seed(11)
     W0 = torch.randn(4 * nq, nq + 2, dtype=torch.float64, device=dev, generator=g)
