@@ -79,5 +79,20 @@ assert np.all(np.isfinite(x.cpu().numpy()))
 Yt = torch.randn(1 << 15, 24, dtype=torch.float64, device="cuda")
 Qt = rla.orth(Yt)
 assert float(torch.linalg.norm(Qt.T @ Qt - torch.eye(24, dtype=torch.float64, device="cuda"))) < 1e-12
+# fused reduce + peer exchange (world = 1: the exchange buffer is this process's own), update-form GEMM on an even pitch
+from parla_b200.parallel import PeerComm
+comm = PeerComm(None, torch.device("cuda", 0), 8193)
+for (m, n) in ((300, 64), (257, 2049), (300, 64)):
+    A4, w4 = dev(rng.standard_normal((m, n))), dev(rng.standard_normal(n))
+    ua, ub = torch.zeros(m, dtype=torch.float64, device="cuda"), torch.zeros(m, dtype=torch.float64, device="cuda")
+    assert torch.equal(K.stream_pass(A4, w=w4, u=ua, flags=3), K.stream_pass(A4, w=w4, u=ub, flags=3, comm=comm))
+torch.cuda.synchronize()
+comm.close()
+Cbuf = torch.zeros(300, 262, dtype=torch.float64, device="cuda")
+Cm2 = rng.standard_normal((300, 261)); Cbuf[:, :261] = dev(Cm2)
+Am2, Bm2 = rng.standard_normal((300, 128)), rng.standard_normal((128, 261))
+Bbuf = torch.zeros(128, 262, dtype=torch.float64, device="cuda"); Bbuf[:, :261] = dev(Bm2)
+K.gemm(dev(Am2), Bbuf[:, :261], alpha=-1.0, beta=1.0, out=Cbuf[:, :261])
+assert np.allclose(Cbuf[:, :261].cpu().numpy(), Cm2 - Am2 @ Bm2) and float(Cbuf[:, 261].abs().sum()) == 0.0
 torch.cuda.synchronize()
 print("sanitize_smoke OK")
