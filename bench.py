@@ -460,7 +460,7 @@ def run_gpu_arm(a):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "stream_pass_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"kernel": "pla::stream_pass_kernel<2,4,2> (fused A w / A^T u, one read of A per LSQR iteration)",
+    roofline = {"kernel": "pla::stream_pass_kernel<2,4,2,256> (fused A w / A^T u, one read of A per LSQR iteration)",
                 "bound": "hbm", "achieved": alg_bytes / t_pass / 1e9 if fused else None, "peak": peak, "unit": "GB/s",
                 "frac": (alg_bytes / t_pass / 1e9 / peak) if fused else None, "traffic": traffic,
                 "peak_source": peak_src, "launches_timed": len(fused), "ms_per_launch": 1e3 * t_pass,
