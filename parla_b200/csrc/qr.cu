@@ -10,6 +10,7 @@
 // reflector is applied).  Trailing matrix: W = V^T C (row-split partials, fixed-order reduction),
 // C -= V (T^T W) with T the compact-WY factor.  Every reduction has a fixed order => deterministic.
 #include <cooperative_groups.h>
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/parla_b200.h"
 
@@ -559,6 +560,9 @@ constexpr int QB_RPC_MAX = 160;              // rows per CTA (shared-memory limi
 constexpr int QB_WLD = QR_NBO - QR_NB;       // 112: leading dimension of the W totals
 constexpr int QB_NV = QR_NB * QB_WLD + QR_NB * QR_NB;   // 2048 values per reduce-scatter
 constexpr int QB_NL = 12;                    // fan-in records per thread (>= QB_MAXG / 16, multiple of 4)
+constexpr int QP_NV = 2 * QR_NB;             // pair steps: 32 values per exchange (dots of TWO columns with the sub-panel)
+constexpr int QP_NL = 20;                    // pair steps: fan-in records per warp (>= QB_MAXG / 8, multiple of 4)
+constexpr double QP_THETA = 0.05;            // look-ahead accepted while |x'_{j+1}|^2 >= theta |x_{j+1}|^2 (see the kernel)
 
 struct __align__(16) LLLine { uint32_t lo, f1, hi, f2; };
 
@@ -622,10 +626,13 @@ struct BlockParams {
     double* tau;                   // the block's JB scalar factors
     double* Vx;                    // out: (M - J0) x 128 explicit reflectors (unit diagonal, zeros above / right of JB)
     int rpc;                       // rows per CTA (multiple of 16)
-    LLLine* ll_step;               // [2][16][QB_MAXG] partials, ONE line per 32-byte sector (stride 2 lines)
-    LLLine* ll_diag;               // [2][16] diagonal-row snapshot (owner -> everybody when G <= 16, -> reducers otherwise)
-    LLLine* ll_tot;                // [2][QB_MAXG][16] per-reader copies of the diagonal row (G > 16)
-    LLLine* ll_fan;                // [2][QB_MAXG readers][QB_MAXG writers][16] pushed partials (G > 16)
+    // (sizes for the pair steps, 32 values per exchange; the one-column steps use the first half of each record)
+    LLLine* ll_step;               // [2][32][QB_MAXG] partials, ONE line per 32-byte sector (stride 2 lines)
+    LLLine* ll_diag;               // [2][32] diagonal-row snapshots (owner -> everybody when G <= 16, -> reducers otherwise)
+    LLLine* ll_tot;                // [2][QB_MAXG][32] per-reader copies of the diagonal rows (G > 16)
+    LLLine* ll_fan;                // [2][QB_MAXG readers][QB_MAXG writers][32] pushed partials (G > 16)
+    int pair;                      // 1: two columns per exchange (look-ahead through Gram identities), 0: one
+    double* gram_part;             // out (or null): [G][36][256] per-CTA partials of striu(Vx^T Vx), see qr_gram_reduce_kernel
     LLLine* ll_bar;                // [2][QB_MAXG]
     LLLine* ll_res;                // [2][QB_NV]
     double* wpart;                 // [G][QB_NV]
@@ -647,6 +654,10 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
     double* wsum = drow + QR_NB;                           // [8][16]
     double* taus = wsum + (QB_THREADS / 32) * QR_NB;       // [16]
     double* tot16 = taus + QR_NB;                          // [32] this CTA's 16 partial sums + its diagonal-row snapshot
+    double* pr = tot16 + 2 * QR_NB;                        // pair steps: [32] totals S0_q | S1_q
+    double* pd = pr + QP_NV;                               //             [32] diagonal rows D0_q | D1_q
+    double* pt = pd + QP_NV;                               //             [64] this CTA's totals | its diagonal-row snapshots
+    double* pw = pt + 2 * QP_NV;                           //             [8][32] per-warp partials
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int G = gridDim.x, b = blockIdx.x, JB = p.JB, rpc = p.rpc;
     const long long rows = p.M - p.J0;
@@ -666,91 +677,116 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
     QB_T(0);
 
     const int c = tid & 15, g = tid >> 4;                  // column of the sub-panel / row group
+    uint32_t xs = 0;                                       // pair steps: exchanges so far in this block (<= JB)
     for (int c0 = 0; c0 < JB; c0 += QR_NB) {
         const int jbp = min(QR_NB, JB - c0);
-        // ---- partial sums for the first column of the sub-panel
-        double part = 0.0;
+        if (p.pair) {
+        // ================= pair steps: ONE exchange serves TWO columns =================================================
+        // Before step j every CTA contributes, over its rows BELOW row gc + 1,
+        //     S0_q = x_j . x_q (q >= j)   and   S1_q = x_{j+1} . x_q (q >= j + 1)
+        // and the owners of rows gc and gc + 1 publish those rows (D0_q, D1_q).  Reflector j follows exactly as in the
+        // one-column step (sigma_j = S0_j + D1_j^2, x_j . x_q = S0_q + D1_j D1_q).  Because H_j is the rank-one update
+        // x_q <- x_q - v wv0_q with v = scale_j x_j below the diagonal, the inner products that reflector j + 1 needs
+        // after H_j follow from the SAME sums:
+        //     T_q = x'_{j+1} . x'_q = S1_q - sc (wv0_q S0_{j+1} + wv0_{j+1} S0_q) + wv0_{j+1} wv0_q sc^2 S0_j,
+        // and row gc + 1 after H_j is D1_q - (sc D1_j) wv0_q.  So both reflectors are known after one exchange and are
+        // applied in one sweep over the rows (x_q -= a wv0_q + a' wv1_q), which also gathers the sums of the next step.
+        // T_{j+1} = |x'_{j+1}|^2 is a difference: if it keeps less than QP_THETA of |x_{j+1}|^2 (column j + 1 almost
+        // parallel to column j) the look-ahead is dropped for this step -- every CTA sees the same numbers and takes
+        // the same decision -- and column j + 1 gets its own exchange with exactly summed norms, as in LAPACK.
+        double part0 = 0.0, part1 = 0.0;
         for (int it = 0; it < nit; ++it) {
             const int r = g + QR_NB * it;
-            if (r < nloc && l0 + r > c0 && c < jbp) part = fma(P[r * QB_LDP + c0], P[r * QB_LDP + c0 + c], part);
+            if (r < nloc && l0 + r > c0 + 1 && c < jbp) {
+                const double xc = P[r * QB_LDP + c0 + c];
+                part0 = fma(P[r * QB_LDP + c0], xc, part0);
+                if (c >= 1) part1 = fma(P[r * QB_LDP + c0 + 1], xc, part1);
+            }
         }
-        for (int j = 0; j < jbp; ++j) {
+        int j = 0;
+        while (j < jbp) {
             const int gc = c0 + j;                         // block-local column == block-local diagonal row
-            const uint32_t epoch = p.epoch_base + (uint32_t)gc;
-            const int par = (int)(epoch & 1u);
-            // The column step is written without intra-warp divergence (uniform loops closed by warp votes, PTX-
-            // predicated stores): a divergent spin in warp 0 made the whole CTA wait thousands of cycles per column.
-            // Exchange = ONE hop through L2 (measured on B200: a line written by one SM is seen by a polling SM after
-            // ~2000 cycles once both dies take part; lines polled by many SMs, or reductions that need a second hop,
-            // cost 4000-8000, see scripts/ll_hop_probe.cu):
-            //   G <= 16 CTAs: each CTA publishes 16 lines, everybody polls all of them (few readers per line);
-            //   G  > 16     : each CTA PUSHES its 16 partials into a private 256-byte record of every reader
-            //                 (fan[par][reader][writer][16]: one writer and one reader per line), a reader polls its
-            //                 own G records with coalesced loads and sums them in CTA order.
-            // Every CTA adds the same numbers in the same order, so beta / tau / scale are bit-identical everywhere.
-            // (1) CTA totals of the 16 quantities
-            part += __shfl_xor_sync(0xffffffffu, part, 16);
-            st_shared_pred(wsum + wid * QR_NB + (lane & 15), part, lane < QR_NB);
+            const uint32_t epoch = p.epoch_base + xs;
+            const int par = (int)(xs & 1u);
+            ++xs;
+            const bool has1 = j + 1 < jbp;
+            const bool row1 = (long long)gc + 1 < rows;
+            const bool own0 = gc >= l0 && gc < l0 + nloc;
+            const bool own1 = gc + 1 >= l0 && gc + 1 < l0 + nloc;
+            // (1) CTA totals of the 32 quantities (lane v: v < 16 -> S0_v / D0_v, v >= 16 -> S1_{v-16} / D1_{v-16})
+            part0 += __shfl_xor_sync(0xffffffffu, part0, 16);
+            part1 += __shfl_xor_sync(0xffffffffu, part1, 16);
+            st_shared_pred(pw + wid * QP_NV + (lane & 15), part0, lane < QR_NB);
+            st_shared_pred(pw + wid * QP_NV + QR_NB + (lane & 15), part1, lane < QR_NB);
             __syncthreads();
-            const bool own = gc >= l0 && gc < l0 + nloc;         // I own the diagonal row: I publish its snapshot
             if (wid == 0) {                                      // warp-uniform
-                const int q = lane & 15;
-                const bool act = lane < QR_NB && q >= j && q < jbp;
+                const int q = lane & 15, hi = lane >> 4;
+                const bool inq = q >= j && q < jbp;
+                const bool actS = hi == 0 ? inq : (has1 && q >= j + 1 && q < jbp);
+                const bool actD = inq && (hi == 0 || row1);
+                const bool ownd = hi == 0 ? own0 : own1;
                 double tot = 0.0;
 #pragma unroll
-                for (int w = 0; w < QB_THREADS / 32; ++w) tot += wsum[w * QR_NB + q];
-                const double dv = P[(own ? (int)(gc - l0) : 0) * QB_LDP + c0 + q];
+                for (int w = 0; w < QB_THREADS / 32; ++w) tot += pw[w * QP_NV + lane];
+                const double dv = P[(ownd ? (int)(gc + hi - l0) : 0) * QB_LDP + c0 + q];
                 if (G <= QR_NB) {
-                    ll_store(p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + b), tot, epoch, act);
-                    ll_store(p.ll_diag + par * QR_NB + q, dv, epoch, act && own);
+                    ll_store(p.ll_step + 2 * (((size_t)(par * QP_NV + lane)) * QB_MAXG + b), tot, epoch, actS);
+                    ll_store(p.ll_diag + par * QP_NV + lane, dv, epoch, actD && ownd);
                 } else {
-                    st_shared_pred(tot16 + q, tot, lane < QR_NB);
-                    st_shared_pred(tot16 + QR_NB + q, dv, lane < QR_NB);
+                    pt[lane] = tot;
+                    pt[QP_NV + lane] = dv;
                 }
             }
             if (G > QR_NB) {
                 __syncthreads();
-                const int q = tid & 15, r0 = tid >> 4;
-                const bool actq = q >= j && q < jbp;
-                const double tv = tot16[q], dv = tot16[QR_NB + q];
-                for (int r = r0; r < G; r += 16) {               // (CTA-uniform trip count up to the predicate)
-                    ll_store(p.ll_fan + (((size_t)(par * QB_MAXG + r)) * QB_MAXG + b) * QR_NB + q, tv, epoch, actq);
-                    ll_store(p.ll_tot + ((size_t)(par * QB_MAXG + r)) * QR_NB + q, dv, epoch, actq && own);
+                const int q = lane & 15, hi = lane >> 4;         // a warp writes one 512-byte record per reader
+                const bool inq = q >= j && q < jbp;
+                const bool actS = hi == 0 ? inq : (has1 && q >= j + 1 && q < jbp);
+                const bool actD = inq && (hi == 0 || row1) && (hi == 0 ? own0 : own1);
+                const double tv = pt[lane], dv = pt[QP_NV + lane];
+                for (int r = wid; r < G; r += QB_THREADS / 32) {
+                    ll_store(p.ll_fan + (((size_t)(par * QB_MAXG + r)) * QB_MAXG + b) * QP_NV + lane, tv, epoch, actS);
+                    ll_store(p.ll_tot + ((size_t)(par * QB_MAXG + r)) * QP_NV + lane, dv, epoch, actD);
                 }
             }
             QB_T(1);
             // (2) gather
             if (G <= QR_NB) {
-                const int q = tid >> 4, slot = tid & 15;
-                const bool act = q >= j && q < jbp && slot < G;
-                const LLLine* line = p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + (slot < G ? slot : 0));
-                double acc = 0.0;
-                bool ok;
-                do {
-                    ok = ll_try_load(line, epoch, acc) || !act;
-                } while (!__all_sync(0xffffffffu, ok));
-                if (!act) acc = 0.0;
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                st_shared_pred(red + q, acc, slot == 0);
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int vq = (tid >> 4) + QR_NB * h2, slot = tid & 15, q = vq & 15;
+                    const bool actS = h2 == 0 ? (q >= j && q < jbp) : (has1 && q >= j + 1 && q < jbp);
+                    const bool act = actS && slot < G;
+                    const LLLine* line = p.ll_step + 2 * (((size_t)(par * QP_NV + vq)) * QB_MAXG + (slot < G ? slot : 0));
+                    double acc = 0.0;
+                    bool ok;
+                    do {
+                        ok = ll_try_load(line, epoch, acc) || !act;
+                    } while (!__all_sync(0xffffffffu, ok));
+                    if (!act) acc = 0.0;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    st_shared_pred(pr + vq, acc, slot == 0);
+                }
             } else {
-                // thread (q, bg): records of CTAs bg, bg + 16, ... ; a warp reads two consecutive 256-byte records
-                const int q = tid & 15, bg = tid >> 4;
-                const bool actq = q >= j && q < jbp;
-                const LLLine* base = p.ll_fan + (((size_t)(par * QB_MAXG + b)) * QB_MAXG + bg) * QR_NB + q;
-                double v[QB_NL];
+                // warp w reads the records of CTAs w, w + 8, ...; its 32 lanes are the 32 values of a record
+                const int q = lane & 15, hi = lane >> 4;
+                const bool actS = hi == 0 ? (q >= j && q < jbp) : (has1 && q >= j + 1 && q < jbp);
+                const LLLine* base = p.ll_fan + (((size_t)(par * QB_MAXG + b)) * QB_MAXG + wid) * QP_NV + lane;
+                double v[QP_NL];
                 unsigned pending = 0;
 #pragma unroll
-                for (int i = 0; i < QB_NL; ++i) {
+                for (int i = 0; i < QP_NL; ++i) {
                     v[i] = 0.0;
-                    if (actq && bg + 16 * i < G) pending |= 1u << i;
+                    if (actS && wid + (QB_THREADS / 32) * i < G) pending |= 1u << i;
                 }
                 do {
 #pragma unroll
-                    for (int g4 = 0; g4 < QB_NL / 4; ++g4) {
+                    for (int g4 = 0; g4 < QP_NL / 4; ++g4) {
                         unsigned long long w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
                         const unsigned m4 = (pending >> (4 * g4)) & 15u;
-                        ll_load4<16 * QR_NB * (int)sizeof(LLLine)>(base + (size_t)64 * QR_NB * g4, m4, w0, w1);
+                        ll_load4<(QB_THREADS / 32) * QP_NV * (int)sizeof(LLLine)>(
+                            base + (size_t)4 * (QB_THREADS / 32) * QP_NV * g4, m4, w0, w1);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             double val;
@@ -761,80 +797,304 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
                 } while (__any_sync(0xffffffffu, pending != 0));
                 double acc = 0.0;
 #pragma unroll
-                for (int i = 0; i < QB_NL; ++i) acc += v[i];
-                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                st_shared_pred(wsum + wid * QR_NB + q, acc, lane < QR_NB);     // (the step's wsum has been consumed)
+                for (int i = 0; i < QP_NL; ++i) acc += v[i];
+                pw[wid * QP_NV + lane] = acc;                                  // (the step's pw has been consumed)
                 __syncthreads();
                 if (wid == 1) {                                                // warp-uniform: fixed-order final sums
                     double tot = 0.0;
 #pragma unroll
-                    for (int w = 0; w < QB_THREADS / 32; ++w) tot += wsum[w * QR_NB + (lane & 15)];
-                    st_shared_pred(red + (lane & 15), tot, lane < QR_NB);
+                    for (int w = 0; w < QB_THREADS / 32; ++w) tot += pw[w * QP_NV + lane];
+                    pr[lane] = tot;
                 }
             }
             if (wid == 0) {
-                // warp-uniform: the diagonal-row snapshot (my private copy when G > 16)
-                const int qd = lane & 15;
-                const bool need = lane < QR_NB && qd >= j && qd < jbp;
-                const LLLine* line = G > QR_NB ? p.ll_tot + ((size_t)(par * QB_MAXG + b)) * QR_NB + qd
-                                               : p.ll_diag + par * QR_NB + qd;
+                // warp-uniform: the two diagonal-row snapshots (my private copies when G > 16)
+                const int q = lane & 15, hi = lane >> 4;
+                const bool need = q >= j && q < jbp && (hi == 0 || row1);
+                const LLLine* line = G > QR_NB ? p.ll_tot + ((size_t)(par * QB_MAXG + b)) * QP_NV + lane
+                                               : p.ll_diag + par * QP_NV + lane;
                 double dv = 0.0;
                 bool ok;
                 do {
                     ok = ll_try_load(line, epoch, dv) || !need;
                 } while (!__all_sync(0xffffffffu, ok));
-                st_shared_pred(drow + qd, dv, need);
+                pd[lane] = need ? dv : 0.0;
             }
             __syncthreads();
             QB_T(2);
-            // (3) reflector j (LAPACK dlarfg), computed redundantly (and bit-identically) by every thread
-            const double sigma = red[j], alpha = drow[j];
-            double beta = alpha, tau = 0.0, scale = 0.0;
-            if (sigma != 0.0) {
-                const double nrm = sqrt(fma(alpha, alpha, sigma));
-                beta = alpha >= 0.0 ? -nrm : nrm;
-                tau = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+            // (3) reflector j (LAPACK dlarfg) and, through the identities above, reflector j + 1 -- computed redundantly
+            //     (and bit-identically) by every thread
+            const double S0j = pr[j], D1j = pd[QR_NB + j], alpha0 = pd[j];
+            const double sigma0 = fma(D1j, D1j, S0j);
+            double beta0 = alpha0, tau0 = 0.0, sc0 = 0.0;
+            if (sigma0 != 0.0) {
+                const double nrm = sqrt(fma(alpha0, alpha0, sigma0));
+                beta0 = alpha0 >= 0.0 ? -nrm : nrm;
+                tau0 = (beta0 - alpha0) / beta0;
+                sc0 = 1.0 / (alpha0 - beta0);
             }
-            st_shared_pred(taus + j, tau, tid == 0);
-            st_global_pred(p.tau + gc, tau, tid == 0 && b == 0);
-            const double wv_c = (c > j && c < jbp) ? tau * fma(scale, red[c], drow[c]) : 0.0;
-            const double wv_n = (j + 1 < jbp) ? tau * fma(scale, red[j + 1], drow[j + 1]) : 0.0;
+            // wv0_q = tau_j (v . x_q), q > j
+            auto wv0 = [&](int q) { return (q > j && q < jbp) ? tau0 * fma(sc0, fma(D1j, pd[QR_NB + q], pr[q]), pd[q]) : 0.0; };
+            const double w0j1 = wv0(j + 1);
+            const double S0j1 = has1 ? pr[j + 1] : 0.0;
+            const double a1 = D1j * sc0;                                       // entry of v_j in row gc + 1
+            // T_q = x'_{j+1} . x'_q over the rows below gc + 1 (q >= j + 1)
+            auto tq = [&](int q, double w0q) {
+                return fma(w0j1 * w0q, sc0 * sc0 * S0j, pr[QR_NB + q] - sc0 * fma(w0q, S0j1, w0j1 * pr[q]));
+            };
+            int adv = 1;
+            double beta1 = 0.0, tau1 = 0.0, sc1 = 0.0, alpha1 = 0.0;
+            if (has1) {
+                alpha1 = fma(-a1, w0j1, pd[QR_NB + j + 1]);
+                const double sigma1 = tq(j + 1, w0j1);
+                if (sigma1 >= QP_THETA * pr[QR_NB + j + 1] && sigma1 >= 0.0) {
+                    adv = 2;
+                    beta1 = alpha1;
+                    if (sigma1 != 0.0) {
+                        const double nrm = sqrt(fma(alpha1, alpha1, sigma1));
+                        beta1 = alpha1 >= 0.0 ? -nrm : nrm;
+                        tau1 = (beta1 - alpha1) / beta1;
+                        sc1 = 1.0 / (alpha1 - beta1);
+                    }
+                }
+            }
+            // wv1_q = tau_{j+1} (v' . x'_q), q > j + 1 (zero when the look-ahead is not taken)
+            auto wv1 = [&](int q, double w0q) {
+                return (adv == 2 && q > j + 1 && q < jbp) ? tau1 * fma(sc1, tq(q, w0q), fma(-a1, w0q, pd[QR_NB + q])) : 0.0;
+            };
+            const int n0 = j + adv, n1 = n0 + 1;                               // the columns of the next step
+            const double w0c = wv0(c), w1c = wv1(c, w0c);
+            const double w0n0 = wv0(n0), w1n0 = wv1(n0, w0n0);
+            const double w0n1 = wv0(n1), w1n1 = wv1(n1, w0n1);
+            st_shared_pred(taus + j, tau0, tid == 0);
+            st_global_pred(p.tau + gc, tau0, tid == 0 && b == 0);
+            st_shared_pred(taus + (has1 ? j + 1 : j), tau1, tid == 0 && adv == 2);
+            st_global_pred(p.tau + gc + 1, tau1, tid == 0 && b == 0 && adv == 2);
             QB_T(10);
-            // (4) apply to my rows; gather the partial sums of column j + 1 on the fly
-            part = 0.0;
-            for (int it0 = 0; it0 < nit; it0 += 4) {           // 4 row sweeps per batch: 12 shared-memory loads in flight
-                double aj[4], an[4], ac[4];
+            // (4) apply to my rows; gather the sums of the next step on the fly
+            part0 = 0.0;
+            part1 = 0.0;
+            const bool two = adv == 2;
+            const bool cn0 = c >= n0 && c < jbp && n0 < jbp, cn1 = c >= n1 && c < jbp && n1 < jbp;
+            // row sweeps in batches of 4 (20 shared-memory loads in flight), then 2, then 1: no padded iterations
+            const int l0i = (int)l0;
+            auto sweep = [&](auto nu_tag, int it0) {
+                constexpr int NU = decltype(nu_tag)::value;
+                double xj[NU], xj1[NU], xc[NU], xn0[NU], xn1[NU];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NU; ++u) {
                     const int r = g + QR_NB * (it0 + u);
-                    const bool valid = it0 + u < nit && r < nloc;
+                    const bool valid = r < nloc;
                     const double* row = P + (valid ? r : 0) * QB_LDP + c0;
-                    aj[u] = valid ? row[j] : 0.0;
-                    an[u] = (valid && j + 1 < jbp) ? row[j + 1] : 0.0;
-                    ac[u] = valid ? row[c] : 0.0;
+                    xj[u] = valid ? row[j] : 0.0;
+                    xj1[u] = (valid && has1) ? row[j + 1] : 0.0;
+                    xc[u] = valid ? row[c] : 0.0;
+                    xn0[u] = (valid && n0 < jbp) ? row[n0] : 0.0;
+                    xn1[u] = (valid && n1 < jbp) ? row[n1] : 0.0;
                 }
                 __syncwarp();                               // every lane has read the old rows before anyone writes
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // branch-free (selects + predicated store): lanes c < j, c == j, c > j and the diagonal row would
-                    // otherwise serialise as separate divergent paths
+                for (int u = 0; u < NU; ++u) {
+                    // branch-free (selects + predicated store), as in the one-column step
                     const int r = g + QR_NB * (it0 + u);
-                    const bool valid = it0 + u < nit && r < nloc;
-                    const long long li = l0 + r;
-                    const bool diag = li == gc;
-                    const double vv = diag ? 1.0 : aj[u] * scale;              // reflector entry of this row
-                    const double anew = fma(-vv, wv_c, ac[u]);                 // (wv_c = 0 for c <= j)
-                    const double out = (c == j) ? (diag ? beta : vv) : anew;
+                    const bool valid = r < nloc;
+                    const int li = l0i + r;
+                    const bool d0 = li == gc, d1 = two && li == gc + 1;
+                    const double a = d0 ? 1.0 : xj[u] * sc0;                   // entry of v_j in this row (rows >= gc)
+                    const double x1p = fma(-a, w0j1, xj1[u]);                  // column j + 1 after H_j
+                    const double a2 = d1 ? 1.0 : ((two && li > gc + 1) ? x1p * sc1 : 0.0);   // entry of v_{j+1}
+                    const double yc = fma(-a2, w1c, fma(-a, w0c, xc[u]));
+                    const double yn0 = fma(-a2, w1n0, fma(-a, w0n0, xn0[u]));
+                    const double yn1 = fma(-a2, w1n1, fma(-a, w0n1, xn1[u]));
+                    double out = yc;
+                    if (c == j) out = d0 ? beta0 : a;
+                    if (two && c == j + 1 && li > gc) out = d1 ? beta1 : a2;
                     if (valid && li >= gc && c >= j && c < jbp) P[r * QB_LDP + c0 + c] = out;
-                    const double x = (c == j + 1) ? anew : fma(-vv, wv_n, an[u]);
-                    const bool cnt = valid && li > gc + 1 && c > j && c < jbp;
-                    part = fma(cnt ? x : 0.0, anew, part);
+                    const bool cnt = valid && li > gc + adv + 1;
+                    part0 = fma((cnt && cn0) ? yn0 : 0.0, yc, part0);
+                    part1 = fma((cnt && cn1) ? yn1 : 0.0, yc, part1);
                 }
+            };
+            {
+                int it0 = 0;
+                for (; it0 + 4 <= nit; it0 += 4) sweep(std::integral_constant<int, 4>{}, it0);
+                if (it0 + 2 <= nit) { sweep(std::integral_constant<int, 2>{}, it0); it0 += 2; }
+                if (it0 < nit) sweep(std::integral_constant<int, 1>{}, it0);
             }
             QB_T(11);
             __syncthreads();
             QB_T(3);
+            j += adv;
+        }
+        } else {
+            // ---- partial sums for the first column of the sub-panel
+            double part = 0.0;
+            for (int it = 0; it < nit; ++it) {
+                const int r = g + QR_NB * it;
+                if (r < nloc && l0 + r > c0 && c < jbp) part = fma(P[r * QB_LDP + c0], P[r * QB_LDP + c0 + c], part);
+            }
+            for (int j = 0; j < jbp; ++j) {
+                const int gc = c0 + j;                         // block-local column == block-local diagonal row
+                const uint32_t epoch = p.epoch_base + (uint32_t)gc;
+                const int par = (int)(epoch & 1u);
+                // The column step is written without intra-warp divergence (uniform loops closed by warp votes, PTX-
+                // predicated stores): a divergent spin in warp 0 made the whole CTA wait thousands of cycles per column.
+                // Exchange = ONE hop through L2 (measured on B200: a line written by one SM is seen by a polling SM after
+                // ~2000 cycles once both dies take part; lines polled by many SMs, or reductions that need a second hop,
+                // cost 4000-8000, see scripts/ll_hop_probe.cu):
+                //   G <= 16 CTAs: each CTA publishes 16 lines, everybody polls all of them (few readers per line);
+                //   G  > 16     : each CTA PUSHES its 16 partials into a private 256-byte record of every reader
+                //                 (fan[par][reader][writer][16]: one writer and one reader per line), a reader polls its
+                //                 own G records with coalesced loads and sums them in CTA order.
+                // Every CTA adds the same numbers in the same order, so beta / tau / scale are bit-identical everywhere.
+                // (1) CTA totals of the 16 quantities
+                part += __shfl_xor_sync(0xffffffffu, part, 16);
+                st_shared_pred(wsum + wid * QR_NB + (lane & 15), part, lane < QR_NB);
+                __syncthreads();
+                const bool own = gc >= l0 && gc < l0 + nloc;         // I own the diagonal row: I publish its snapshot
+                if (wid == 0) {                                      // warp-uniform
+                    const int q = lane & 15;
+                    const bool act = lane < QR_NB && q >= j && q < jbp;
+                    double tot = 0.0;
+    #pragma unroll
+                    for (int w = 0; w < QB_THREADS / 32; ++w) tot += wsum[w * QR_NB + q];
+                    const double dv = P[(own ? (int)(gc - l0) : 0) * QB_LDP + c0 + q];
+                    if (G <= QR_NB) {
+                        ll_store(p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + b), tot, epoch, act);
+                        ll_store(p.ll_diag + par * QR_NB + q, dv, epoch, act && own);
+                    } else {
+                        st_shared_pred(tot16 + q, tot, lane < QR_NB);
+                        st_shared_pred(tot16 + QR_NB + q, dv, lane < QR_NB);
+                    }
+                }
+                if (G > QR_NB) {
+                    __syncthreads();
+                    const int q = tid & 15, r0 = tid >> 4;
+                    const bool actq = q >= j && q < jbp;
+                    const double tv = tot16[q], dv = tot16[QR_NB + q];
+                    for (int r = r0; r < G; r += 16) {               // (CTA-uniform trip count up to the predicate)
+                        ll_store(p.ll_fan + (((size_t)(par * QB_MAXG + r)) * QB_MAXG + b) * QR_NB + q, tv, epoch, actq);
+                        ll_store(p.ll_tot + ((size_t)(par * QB_MAXG + r)) * QR_NB + q, dv, epoch, actq && own);
+                    }
+                }
+                QB_T(1);
+                // (2) gather
+                if (G <= QR_NB) {
+                    const int q = tid >> 4, slot = tid & 15;
+                    const bool act = q >= j && q < jbp && slot < G;
+                    const LLLine* line = p.ll_step + 2 * (((size_t)(par * QR_NB + q)) * QB_MAXG + (slot < G ? slot : 0));
+                    double acc = 0.0;
+                    bool ok;
+                    do {
+                        ok = ll_try_load(line, epoch, acc) || !act;
+                    } while (!__all_sync(0xffffffffu, ok));
+                    if (!act) acc = 0.0;
+    #pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    st_shared_pred(red + q, acc, slot == 0);
+                } else {
+                    // thread (q, bg): records of CTAs bg, bg + 16, ... ; a warp reads two consecutive 256-byte records
+                    const int q = tid & 15, bg = tid >> 4;
+                    const bool actq = q >= j && q < jbp;
+                    const LLLine* base = p.ll_fan + (((size_t)(par * QB_MAXG + b)) * QB_MAXG + bg) * QR_NB + q;
+                    double v[QB_NL];
+                    unsigned pending = 0;
+    #pragma unroll
+                    for (int i = 0; i < QB_NL; ++i) {
+                        v[i] = 0.0;
+                        if (actq && bg + 16 * i < G) pending |= 1u << i;
+                    }
+                    do {
+    #pragma unroll
+                        for (int g4 = 0; g4 < QB_NL / 4; ++g4) {
+                            unsigned long long w0[4] = {0, 0, 0, 0}, w1[4] = {0, 0, 0, 0};
+                            const unsigned m4 = (pending >> (4 * g4)) & 15u;
+                            ll_load4<16 * QR_NB * (int)sizeof(LLLine)>(base + (size_t)64 * QR_NB * g4, m4, w0, w1);
+    #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                double val;
+                                const bool got = ll_ready(w0[i], w1[i], epoch, val) && ((m4 >> i) & 1u);
+                                if (got) { v[4 * g4 + i] = val; pending &= ~(1u << (4 * g4 + i)); }
+                            }
+                        }
+                    } while (__any_sync(0xffffffffu, pending != 0));
+                    double acc = 0.0;
+    #pragma unroll
+                    for (int i = 0; i < QB_NL; ++i) acc += v[i];
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    st_shared_pred(wsum + wid * QR_NB + q, acc, lane < QR_NB);     // (the step's wsum has been consumed)
+                    __syncthreads();
+                    if (wid == 1) {                                                // warp-uniform: fixed-order final sums
+                        double tot = 0.0;
+    #pragma unroll
+                        for (int w = 0; w < QB_THREADS / 32; ++w) tot += wsum[w * QR_NB + (lane & 15)];
+                        st_shared_pred(red + (lane & 15), tot, lane < QR_NB);
+                    }
+                }
+                if (wid == 0) {
+                    // warp-uniform: the diagonal-row snapshot (my private copy when G > 16)
+                    const int qd = lane & 15;
+                    const bool need = lane < QR_NB && qd >= j && qd < jbp;
+                    const LLLine* line = G > QR_NB ? p.ll_tot + ((size_t)(par * QB_MAXG + b)) * QR_NB + qd
+                                                   : p.ll_diag + par * QR_NB + qd;
+                    double dv = 0.0;
+                    bool ok;
+                    do {
+                        ok = ll_try_load(line, epoch, dv) || !need;
+                    } while (!__all_sync(0xffffffffu, ok));
+                    st_shared_pred(drow + qd, dv, need);
+                }
+                __syncthreads();
+                QB_T(2);
+                // (3) reflector j (LAPACK dlarfg), computed redundantly (and bit-identically) by every thread
+                const double sigma = red[j], alpha = drow[j];
+                double beta = alpha, tau = 0.0, scale = 0.0;
+                if (sigma != 0.0) {
+                    const double nrm = sqrt(fma(alpha, alpha, sigma));
+                    beta = alpha >= 0.0 ? -nrm : nrm;
+                    tau = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                st_shared_pred(taus + j, tau, tid == 0);
+                st_global_pred(p.tau + gc, tau, tid == 0 && b == 0);
+                const double wv_c = (c > j && c < jbp) ? tau * fma(scale, red[c], drow[c]) : 0.0;
+                const double wv_n = (j + 1 < jbp) ? tau * fma(scale, red[j + 1], drow[j + 1]) : 0.0;
+                QB_T(10);
+                // (4) apply to my rows; gather the partial sums of column j + 1 on the fly
+                part = 0.0;
+                for (int it0 = 0; it0 < nit; it0 += 4) {           // 4 row sweeps per batch: 12 shared-memory loads in flight
+                    double aj[4], an[4], ac[4];
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = g + QR_NB * (it0 + u);
+                        const bool valid = it0 + u < nit && r < nloc;
+                        const double* row = P + (valid ? r : 0) * QB_LDP + c0;
+                        aj[u] = valid ? row[j] : 0.0;
+                        an[u] = (valid && j + 1 < jbp) ? row[j + 1] : 0.0;
+                        ac[u] = valid ? row[c] : 0.0;
+                    }
+                    __syncwarp();                               // every lane has read the old rows before anyone writes
+    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        // branch-free (selects + predicated store): lanes c < j, c == j, c > j and the diagonal row would
+                        // otherwise serialise as separate divergent paths
+                        const int r = g + QR_NB * (it0 + u);
+                        const bool valid = it0 + u < nit && r < nloc;
+                        const long long li = l0 + r;
+                        const bool diag = li == gc;
+                        const double vv = diag ? 1.0 : aj[u] * scale;              // reflector entry of this row
+                        const double anew = fma(-vv, wv_c, ac[u]);                 // (wv_c = 0 for c <= j)
+                        const double out = (c == j) ? (diag ? beta : vv) : anew;
+                        if (valid && li >= gc && c >= j && c < jbp) P[r * QB_LDP + c0 + c] = out;
+                        const double x = (c == j + 1) ? anew : fma(-vv, wv_n, an[u]);
+                        const bool cnt = valid && li > gc + 1 && c > j && c < jbp;
+                        part = fma(cnt ? x : 0.0, anew, part);
+                    }
+                }
+                QB_T(11);
+                __syncthreads();
+                QB_T(3);
+            }
         }
         if (tid >= jbp && tid < QR_NB) taus[tid] = 0.0;
 
@@ -1007,12 +1267,58 @@ __global__ void __launch_bounds__(QB_THREADS, 1) qr_block_coop_kernel(const Bloc
         const int r = idx >> 7, cc = idx & (QR_NBO - 1);
         const long long li = l0 + r;
         const double v = P[r * QB_LDP + cc];
+        const double vx = (cc < JB) ? (li > cc ? v : (li == cc ? 1.0 : 0.0)) : 0.0;
         if (cc < JB) Ablk[li * p.lda + cc] = v;
-        if (p.Vx != nullptr) p.Vx[li * QR_NBO + cc] = (cc < JB) ? (li > cc ? v : (li == cc ? 1.0 : 0.0)) : 0.0;
+        if (p.Vx != nullptr) p.Vx[li * QR_NBO + cc] = vx;
+        P[r * QB_LDP + cc] = vx;                           // the slice now holds the explicit reflectors
+    }
+    // ---- my rows' share of the Gram matrix Vx^T Vx (the substitution kernel of the outer level needs its strict
+    // upper triangle): the 36 blocks (bi <= bj) of 16 x 16, thread (ti, tj) owns entry (ti, tj) of every block.
+    // A separate 128 x 128 x rows GEMM cost 55-65 us per block (one output tile, split-K + reduce); here the flops
+    // ride on SMs that hold the reflectors in shared memory anyway (~4 us), a small kernel adds the G partials.
+    if (p.gram_part != nullptr) {
+        __syncthreads();
+        const int ti = tid >> 4, tj = tid & 15;
+        double acc[36];
+#pragma unroll
+        for (int e = 0; e < 36; ++e) acc[e] = 0.0;
+        for (int r = 0; r < nloc; ++r) {
+            const double* row = P + r * QB_LDP;
+            double va[8], vb[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { va[k] = row[16 * k + ti]; vb[k] = row[16 * k + tj]; }
+            int e = 0;
+#pragma unroll
+            for (int bi = 0; bi < 8; ++bi)
+#pragma unroll
+                for (int bj = bi; bj < 8; ++bj) { acc[e] = fma(va[bi], vb[bj], acc[e]); ++e; }
+        }
+        double* gp = p.gram_part + (size_t)b * 36 * QB_THREADS + tid;
+#pragma unroll
+        for (int e = 0; e < 36; ++e) gp[(size_t)e * QB_THREADS] = acc[e];
     }
     QB_T(9);
     if (p.prof != nullptr && tid == 0)
         for (int i = 0; i < QB_NPROF; ++i) p.prof[(size_t)b * QB_NPROF + i] = pacc[i];
+}
+
+// Gm[16 bi + ti][16 bj + tj] = sum over the G CTAs (fixed order) of the partials qr_block_coop_kernel left, for the 36
+// blocks bi <= bj; the strictly lower blocks are never read (qr_w2_kernel uses striu(Gm)).  36 CTAs x 256 threads.
+__global__ void __launch_bounds__(QB_THREADS) qr_gram_reduce_kernel(const double* __restrict__ part, int G, double* __restrict__ Gm) {
+    const int e = blockIdx.x, tid = threadIdx.x;
+    int bi = 0, rem = e;
+    while (rem >= 8 - bi) { rem -= 8 - bi; ++bi; }
+    const int bj = bi + rem;
+    const double* src = part + (size_t)e * QB_THREADS + tid;
+    double acc = 0.0;
+    int g = 0;
+    for (; g + 4 <= G; g += 4) {
+        const double t0 = src[(size_t)g * 36 * QB_THREADS], t1 = src[(size_t)(g + 1) * 36 * QB_THREADS];
+        const double t2 = src[(size_t)(g + 2) * 36 * QB_THREADS], t3 = src[(size_t)(g + 3) * 36 * QB_THREADS];
+        acc += (t0 + t1) + (t2 + t3);
+    }
+    for (; g < G; ++g) acc += src[(size_t)g * 36 * QB_THREADS];
+    Gm[(size_t)(16 * bi + (tid >> 4)) * QR_NBO + 16 * bj + (tid & 15)] = acc;
 }
 
 // W2 = op(T) W for the compact-WY factor of a block of <= 128 reflectors, T given implicitly by the Gram matrix
@@ -1104,6 +1410,7 @@ struct QrWs {
     LLLine* ll;              // LL lines of the cooperative block kernel: step | diag | bar | res
     size_t ll_bytes;
     double* cpart;           // [QB_MAXG][QB_NV] reduce-scatter partials
+    double* gram_part;       // [QB_MAXG][36][256] per-CTA partials of the block's Gram matrix
     long long* prof;         // [QB_MAXG][QB_NPROF] debug cycle counters
     double* Wbig;            // 128 x (N + 1)
     double* W2big;           // 128 x (N + 1)
@@ -1126,10 +1433,11 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
     const size_t o_w2s = take((size_t)QR_NB * (size_t)(N > 0 ? N : 1) * 8);
     const size_t o_vx = take((size_t)M * QR_NBO * 8);
     const size_t o_gb = take((size_t)QR_NBO * QR_NBO * 8);
-    const size_t ll_lines = (size_t)4 * QR_NB * QB_MAXG + 2 * QR_NB + (size_t)2 * QB_MAXG * QR_NB + 2 * QB_MAXG + 2 * QB_NV +
-                            (size_t)2 * QB_MAXG * QB_MAXG * QR_NB;
+    const size_t ll_lines = (size_t)4 * QP_NV * QB_MAXG + 2 * QP_NV + (size_t)2 * QB_MAXG * QP_NV + 2 * QB_MAXG + 2 * QB_NV +
+                            (size_t)2 * QB_MAXG * QB_MAXG * QP_NV;
     const size_t o_ll = take(ll_lines * sizeof(LLLine));
     const size_t o_cp = take((size_t)QB_MAXG * QB_NV * 8);
+    const size_t o_gp = take((size_t)QB_MAXG * 36 * QB_THREADS * 8);
     const size_t o_pf = take((size_t)QB_MAXG * QB_NPROF * 8);
     const size_t o_wb = take((size_t)QR_NBO * (size_t)(N + 1) * 8);        // even pitch: nc + (nc & 1) <= N + 1
     const size_t o_w2 = take((size_t)QR_NBO * (size_t)(N + 1) * 8);
@@ -1151,6 +1459,7 @@ static size_t qr_ws_layout(long long M, long long N, void* base, QrWs* out) {
         out->ll = (LLLine*)(b + o_ll);
         out->ll_bytes = ll_lines * sizeof(LLLine);
         out->cpart = (double*)(b + o_cp);
+        out->gram_part = (double*)(b + o_gp);
         out->prof = (long long*)(b + o_pf);
         out->Wbig = (double*)(b + o_wb);
         out->W2big = (double*)(b + o_w2);
@@ -1244,9 +1553,11 @@ using namespace pla;
 extern "C" size_t pla_qr_workspace_bytes(int64_t M, int64_t N) { return qr_ws_layout(M, N, nullptr, nullptr); }
 
 // Cooperative factorisation of the block (J0, JB); returns 1 when the block does not fit (caller falls back).
+// *gram_ctas = number of CTAs whose Gram partials are in w.gram_part afterwards (0: none, use the GEMM).
 static int run_block_coop(double* A, long long lda, long long M, long long J0, long long C0, int JB, double* tau_blk,
-                          const QrWs& w, uint32_t epoch_base, cudaStream_t st) {
-    static const int target = [] { const char* e = getenv("PLA_QR_RPC"); int v = e ? atoi(e) : 96; return v < 16 ? 96 : v; }();
+                          const QrWs& w, uint32_t epoch_base, cudaStream_t st, int* gram_ctas) {
+    *gram_ctas = 0;
+    static const int target = [] { const char* e = getenv("PLA_QR_RPC"); int v = e ? atoi(e) : 64; return v < 16 ? 64 : v; }();
     const long long rows = M - J0;
     const int sms = num_sms() < QB_MAXG ? num_sms() : QB_MAXG;
     long long G = (rows + target - 1) / target;
@@ -1259,17 +1570,22 @@ static int run_block_coop(double* A, long long lda, long long M, long long J0, l
     BlockParams bp;
     bp.A = A; bp.lda = lda; bp.M = M; bp.J0 = J0; bp.C0 = C0; bp.JB = JB; bp.tau = tau_blk; bp.Vx = w.Vx; bp.rpc = (int)rpc;
     bp.ll_step = w.ll;
-    bp.ll_diag = bp.ll_step + (size_t)4 * QR_NB * QB_MAXG;
-    bp.ll_tot = bp.ll_diag + 2 * QR_NB;
-    bp.ll_bar = bp.ll_tot + (size_t)2 * QB_MAXG * QR_NB;
+    bp.ll_diag = bp.ll_step + (size_t)4 * QP_NV * QB_MAXG;
+    bp.ll_tot = bp.ll_diag + 2 * QP_NV;
+    bp.ll_bar = bp.ll_tot + (size_t)2 * QB_MAXG * QP_NV;
     bp.ll_res = bp.ll_bar + 2 * QB_MAXG;
     bp.ll_fan = bp.ll_res + 2 * QB_NV;
     bp.wpart = w.cpart;
     bp.epoch_base = epoch_base;
+    static const bool pair = [] { const char* e = getenv("PLA_QR_PAIR"); return !(e && e[0] == '0'); }();
+    bp.pair = pair ? 1 : 0;
+    static const bool gram_in = [] { const char* e = getenv("PLA_QR_GRAM"); return !(e && e[0] == '0'); }();
+    bp.gram_part = (gram_in && w.Vx != nullptr) ? w.gram_part : nullptr;
+    *gram_ctas = bp.gram_part != nullptr ? (int)G : 0;
     static const bool prof = [] { const char* e = getenv("PLA_QR_PROF"); return e && e[0] == '1'; }();
     bp.prof = prof ? w.prof : nullptr;
     const size_t smem = ((size_t)rpc * QB_LDP + (size_t)rpc * QR_NB + QR_NB * QB_WLD + QR_NB * QR_NB + 3 * QR_NB +
-                         (QB_THREADS / 32) * QR_NB + 2 * QR_NB) * sizeof(double);
+                         (QB_THREADS / 32) * QR_NB + 2 * QR_NB + 4 * QP_NV + (QB_THREADS / 32) * QP_NV) * sizeof(double);
     PLA_CUDA(cudaFuncSetAttribute(qr_block_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {(void*)&bp};
     PLA_CUDA(cudaLaunchCooperativeKernel((const void*)qr_block_coop_kernel, dim3((unsigned)G), dim3(QB_THREADS), args,
@@ -1294,8 +1610,13 @@ static int run_block_coop(double* A, long long lda, long long M, long long J0, l
 
 // Explicit reflectors Vx of block (J0, JB) (unless the cooperative kernel already wrote them) and their Gram matrix.
 static int build_block_reflector(const double* A, long long lda, long long M, long long J0, int JB, bool have_vx,
-                                 const QrWs& w, cudaStream_t st) {
+                                 const QrWs& w, cudaStream_t st, int gram_ctas = 0) {
     const long long rows = M - J0;
+    if (have_vx && gram_ctas > 0) {          // the cooperative kernel left per-CTA partials of the Gram matrix
+        qr_gram_reduce_kernel<<<36, QB_THREADS, 0, st>>>(w.gram_part, gram_ctas, w.Gbig);
+        PLA_LAUNCH_CHECK();
+        return 0;
+    }
     if (!have_vx) {
         int nb = (int)((rows * QR_NBO + 255) / 256);
         if (nb > 8 * num_sms()) nb = 8 * num_sms();
@@ -1343,12 +1664,13 @@ extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64
         const int JB = (int)((ncols_factor - J0) < QR_NBO ? (ncols_factor - J0) : QR_NBO);
         const long long nc = N - (J0 + JB);
         bool done = false;
+        int gram_ctas = 0;
         if (use_coop) {
             if (!ll_clean) {                 // epochs restart with every factorisation: stale lines must not match
                 PLA_CUDA(cudaMemsetAsync(w.ll, 0, w.ll_bytes, st));
                 ll_clean = true;
             }
-            const int rc = run_block_coop(A, lda, M, J0, J0, JB, tau + J0, w, (blk + 1u) * 256u, st);
+            const int rc = run_block_coop(A, lda, M, J0, J0, JB, tau + J0, w, (blk + 1u) * 256u, st, &gram_ctas);
             if (rc < 0 || rc > 1) return rc;
             done = (rc == 0);
         }
@@ -1364,7 +1686,7 @@ extern "C" int pla_geqrf_f64(double* A, int64_t M, int64_t N, int64_t lda, int64
         }
         // outer level: the whole block reflector hits the remaining columns through the tensor cores
         if (nc > 0) {
-            int rc = build_block_reflector(A, lda, M, J0, JB, done, w, st);
+            int rc = build_block_reflector(A, lda, M, J0, JB, done, w, st, done ? gram_ctas : 0);
             if (rc) return rc;
             rc = apply_block_reflector(M, J0, JB, tau + J0, A + J0 + JB, lda, nc, /*T^T*/ 1, w, st);
             if (rc) return rc;
@@ -1387,10 +1709,11 @@ extern "C" int pla_qr_factor_block_f64(double* A, int64_t M, int64_t lda, int64_
     qr_ws_layout(M, n_layout, ws, &w);
     cudaStream_t st = (cudaStream_t)stream;
     if (block_index == 0) PLA_CUDA(cudaMemsetAsync(w.ll, 0, w.ll_bytes, st));
-    int rc = run_block_coop(A, lda, M, r0, c0, (int)jb, tau_blk, w, ((uint32_t)block_index + 1u) * 256u, st);
+    int gram_ctas = 0;
+    int rc = run_block_coop(A, lda, M, r0, c0, (int)jb, tau_blk, w, ((uint32_t)block_index + 1u) * 256u, st, &gram_ctas);
     if (rc == 1) { set_error("pla_qr_factor_block_f64: %lld rows do not fit the cooperative block kernel", (long long)(M - r0)); return -2; }
     if (rc) return rc;
-    return build_block_reflector(A, lda, M, r0, (int)jb, true, w, st);
+    return build_block_reflector(A, lda, M, r0, (int)jb, true, w, st, gram_ctas);
 }
 
 extern "C" int pla_qr_apply_block_f64(int64_t M, int64_t r0, int64_t jb, const double* tau_blk, double* C, int64_t ldc,

@@ -36,7 +36,7 @@ for (M, N) in [(2000, 501), (4096, 1025), (8192, 2049), (10000, 2001), (16384, 4
     flops = 2.0 * M * nf * nf - 2.0 * nf ** 3 / 3
     rec = {"op": "geqrf", "M": M, "N": N, "ms_best": min(ts), "ms_median": sorted(ts)[len(ts) // 2],
            "tflops": flops / min(ts) / 1e9, "errR_vs_cusolver": errR, "err_lstsq": errx,
-           "coop": os.environ.get("PLA_QR_COOP", "1"), "rpc": os.environ.get("PLA_QR_RPC", "96"), "pitch": ld}
+           "coop": os.environ.get("PLA_QR_COOP", "1"), "rpc": os.environ.get("PLA_QR_RPC", "64"), "pitch": ld}
     print(json.dumps(rec), flush=True)
 # orth (geqrf + orgqr) of a tall-skinny block, as in the low-rank path
 for (M, N) in [(1 << 17, 128), (1 << 20, 512)]:
