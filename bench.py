@@ -89,14 +89,22 @@ def workload_name(a, world):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+_CPU_SAMPLE = {}
+
+
 def cpu_solve_sample(n, rows, seed=0):
     """One oracle (numpy/scipy port of the reference) SPO solve on a `rows` x n sample of the
     workload; returns the phase times.  All host BLAS threads."""
     import numpy as np
     from oracle import parla_oracle as orc
-    rng = np.random.default_rng(seed)
-    A = rng.standard_normal((rows, n))
-    b = A @ rng.standard_normal(n) + 0.1 * rng.standard_normal(rows)
+    if (n, rows) not in _CPU_SAMPLE:
+        # one synthetic system per run (generating 2^18 x 2048 normals takes as long as solving it); the steps differ
+        # in the sketching operator's seed, like the GPU arm's
+        rng = np.random.default_rng(0)
+        A = rng.standard_normal((rows, n))
+        _CPU_SAMPLE.clear()
+        _CPU_SAMPLE[(n, rows)] = (A, A @ rng.standard_normal(n) + 0.1 * rng.standard_normal(rows))
+    A, b = _CPU_SAMPLE[(n, rows)]
     x, log = orc.SPO(orc.SkOpSJ(VEC_NNZ), SF, MODE)(A, b, 0.0, TOL, ITER_LIM, np.random.default_rng(seed + 1))
     return dict(sketch=log.time_sketch, factor=log.time_factor, presolve=log.time_presolve,
                 iterate=log.time_iterate, iters=int(log.errors.size - 1))

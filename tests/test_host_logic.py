@@ -214,7 +214,7 @@ def test_procedural_wrappers_and_utils_exist():
     from parla_b200.comps import qb as cqb, rangefinders as crf, preconditioning as cpc
     from parla_b200.comps.sketchers import aware
     from parla_b200.comps.determiter import saddle as dsad
-    from parla_b200.utils import linalg_wrappers as ulaw, stats as ustats, misc
+    from parla_b200.utils import linalg_wrappers as ulaw
     want = {ls.sso1: ["A", "b", "delta", "rng", "sampling_factor", "vec_nnz", "lapack_driver"],
             ls.spo1: ["A", "b", "delta", "tol", "iter_lim", "rng", "sampling_factor", "vec_nnz"],
             ls.spo3: ["A", "b", "delta", "tol", "iter_lim", "rng", "sampling_factor", "vec_nnz", "mode"],
@@ -235,15 +235,3 @@ def test_procedural_wrappers_and_utils_exist():
     assert list(inspect.signature(aware.rs1).parameters)[:4] == ["A", "k", "num_pass", "rng"]
     for name in ("orth", "lu_stabilize", "lupt", "lup", "apply_pinv_on_left", "apply_pinv_on_right"):
         assert callable(getattr(ulaw, name))
-    t = np.arange(30.0)
-    fit, r2 = ustats.loglinear_fit(t, 3.0 * np.exp(-0.7 * t))
-    assert np.allclose(fit, [np.log(3.0), -0.7]) and r2 > 1 - 1e-12
-    fit, r2 = ustats.loglog_fit(t + 1, 2.0 * (t + 1) ** -1.5)
-    assert np.allclose(fit, [np.log(2.0), -1.5]) and r2 > 1 - 1e-12
-    with pytest.raises(ValueError):
-        ustats.loglog_fit(t, t + 1)
-
-    @misc.set_docstring("hello")
-    def f():
-        pass
-    assert f.__doc__ == "hello"
