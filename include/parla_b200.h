@@ -55,6 +55,12 @@ int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_t lda, cons
                         const double* g, const double* sc_dev, double sa, double su, double* zss, int flags,
                         const int* istop_dev, void* ws, size_t ws_bytes, void* stream);
 
+/* The same pass WITHOUT its reduce launch: the per-(CTA, group) partials of [z | |u|^2] stay in `ws`
+ * (parts_out[0] of them; partial b of z is ws[b * n .. b * n + n), the |u|^2 partials start at double index
+ * parts_out[1]) for pla_lsqr_fused_step_f64, which sums them in the same order.  parts_out is HOST memory [2]. */
+int pla_stream_pass_parts_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
+                              const double* g, const double* sc_dev, double sa, double su, int flags,
+                              const int* istop_dev, void* ws, size_t ws_bytes, int64_t* parts_out, void* stream);
 /* Row-sharded A (one process per GPU of a node): the same pass, with the sum over the ranks of
  * zss = [z | |u|^2] (the reference has no counterpart: its `np.dot(A.T, u)` at preconditioning.py:34 sees all rows)
  * fused into the reduce kernel as a one-shot all-reduce over NVLink peer memory instead of a separate NCCL call:
@@ -138,6 +144,17 @@ int pla_lsqr_init_f64(int64_t n, const double* t, const double* zss, const doubl
                       double* w, double* dstate, int* istate, void* stream);
 int pla_lsqr_step_f64(int64_t n, const double* t, const double* zss, double* x, double* v, double* w,
                       double* dstate, int* istate, double* arnorm_hist, void* stream);
+/* One launch for everything of an LSQR iteration that is not the pass over A, for small dense preconditioners
+ * M (n_in x r, row-major, r <= 2048, n_in <= 4096; single GPU, delta == 0) -- parla/comps/preconditioning.py:28,37
+ * and determiter/lsqr.py:421-526 of one iteration:
+ *   [z | |u~|^2] = sum of the partials pla_stream_pass_parts_f64 left in pass_ws (nparts == 0: read from zss)
+ *   t = M^T z ;  the step of pla_lsqr_step_f64 on (x, v, w, dstate, istate) ;  xw = M v_new  (the next pass's `w`)
+ * ONE thread-block cluster of 8 CTAs: each owns a row slice of M, partials of t are exchanged through distributed
+ * shared memory, the n-vector step is done redundantly by every CTA (identical arithmetic), CTA 0 writes back.
+ * A no-op once istate[PLA_LSQR_ISTOP] != 0.                                                                   */
+int pla_lsqr_fused_step_f64(int64_t n_in, int64_t r, const double* M, int64_t ldm, const double* pass_ws,
+                            int64_t nparts, int64_t ss_offset, double* zss, double* t, double* x, double* v,
+                            double* w, double* xw, double* dstate, int* istate, double* arnorm_hist, void* stream);
 /* LSQR on the adjoint operator A_pc^T (under-determined branch of PcSS2, saddle.py:203-214; SPU1,
  * least_squares.py:425-494): short vector u (length r), long vectors v~, w, x (length of A's rows).
  *   init  : u = c_pc / |c_pc|

@@ -23,6 +23,8 @@ SIGNATURES = {
     "pla_stream_pass_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "pla_stream_pass_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_int,
                                     c_vp, c_vp, c_sz, c_vp]),
+    "pla_stream_pass_parts_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_int,
+                                          c_vp, c_vp, c_sz, c_vp, c_vp]),
     "pla_stream_pass_peer_f64": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_int,
                                          c_vp, c_vp, c_sz, c_vp, c_int, c_int, c_i64, C.c_uint32, c_vp]),
     "pla_peer_exchange_bytes": (c_sz, [c_int, c_i64]),
@@ -37,6 +39,8 @@ SIGNATURES = {
     "pla_lsqr_init_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_vp]),
     "pla_lsqr_step_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pla_lsqr_fused_step_f64": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pla_lsqr_ridge_f64": (c_int, [c_i64, c_dbl, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
     "pla_lsqr_under_init_f64": (c_int, [c_i64, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp]),
     "pla_lsqr_under_init2_f64": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),

@@ -26,6 +26,11 @@ _POLL_CACHE = {}
 GRAPH_MAX_ELEMS = int(os.environ.get("PLA_LSQR_GRAPH_MAX_ELEMS", 1 << 27))
 USE_GRAPH = os.environ.get("PLA_LSQR_GRAPH", "0") == "1"
 _CAPTURE_STREAMS = {}
+# Fused vector phase (PLA_LSQR_FUSED, default on): for a small dense preconditioner on one GPU the six launches
+# between two passes over A (reduce, M^T z + its reduce + copy, recurrences, M v) become one cluster kernel,
+# K.lsqr_fused_step -- at 2^16 x 500 they cost more than the pass itself (profiles/r2_cfg1_final.jsonl).
+FUSED_MAX_ELEMS = int(os.environ.get("PLA_LSQR_FUSED_MAX_ELEMS", 1 << 20))
+USE_FUSED = os.environ.get("PLA_LSQR_FUSED", "1") != "0"
 
 
 def _capture_iteration(dev, n_max, body):
@@ -111,11 +116,21 @@ def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=F
         A.bidiag_pass(v, u, ub, zss, xw, t, sc=sc, istop=istop_dev)
         K.lsqr_step(t, zs, x, v, w, dstate, istate, hist)
 
+    fused = USE_FUSED and A.fusable(FUSED_MAX_ELEMS)
+
+    def iteration_fused():              # xw = M v is already there: the previous fused step (or the prologue) left it
+        ws, nparts, ss_off = K.stream_pass_parts(A.A, w=xw, u=u, sc=sc, istop=istop_dev)
+        A.passes += 1
+        K.lsqr_fused_step(A.R, ws, nparts, ss_off, zss, t, x, v, w, xw, dstate, istate, hist)
+
     post(0)
     events[0].synchronize()
     launched = 0
     if int(pinned[0][0]) == 0:
         graph = None
+        if fused:
+            A.precond(v, out=xw, istop=istop_dev)
+            iteration = iteration_fused
         if USE_GRAPH and A.group is None and A.m_local * A.n <= GRAPH_MAX_ELEMS and iter_lim > 2:
             passes0 = A.passes
             graph, nodes = _capture_iteration(dev, max(A.n, n), iteration)

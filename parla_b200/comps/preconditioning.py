@@ -42,6 +42,15 @@ class PrecondOperator:
         # kernel (NVLink peer memory); otherwise (None) an NCCL all-reduce follows the pass
         self.comm = peer_comm(self.group, self.A.device) if self.A.is_cuda else None
 
+    def fusable(self, max_elems):
+        """True when K.lsqr_fused_step can stand in for reduce -> M^T z -> step -> M v: one GPU, no ridge rows, a small
+        dense row-major M, and an A the plain (not column-blocked) streaming pass handles."""
+        n, r = self.n, self.rank
+        return (self.group is None and self.comm is None and self.delta == 0 and not self.tri
+                and self.R.dim() == 2 and self.R.shape == (n, r) and self.R.stride(1) == 1 and self.R.stride(0) >= r
+                and n * r <= max_elems and r <= K.FUSED_MAX_R and n <= K.FUSED_MAX_NIN
+                and n <= K.PASS_MAX_N and not (n % 2 == 1 and n > K.PASS_MAX_N // 2))
+
     def _pass(self, **kw):
         """One streaming pass over this rank's rows; ``zss`` comes back summed over the ranks."""
         zss = K.stream_pass(self.A, comm=self.comm, **kw)

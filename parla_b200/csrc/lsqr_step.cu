@@ -6,8 +6,11 @@
 //   lsqr.py:421-425  u = A v - alfa u ; beta = |u| ; u /= beta      ->  pass with (sa, su) = (1, -alfa/beta_prev)
 //   lsqr.py:427      v = A^T u - beta v                             ->  t / beta - beta v   (linearity)
 // so the only quantities needed here are t = M^T A^T u~ and |u~|^2.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/parla_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace pla {
 
@@ -81,55 +84,12 @@ __global__ void __launch_bounds__(LS_THREADS) lsqr_init_kernel(long long n, cons
     }
 }
 
-__global__ void __launch_bounds__(LS_THREADS) lsqr_step_kernel(long long n, const double* __restrict__ t,
-                                                               const double* __restrict__ zss, double* x, double* v,
-                                                               double* w, double* ds, int* is, double* hist) {
-    if (is[PLA_LSQR_ISTOP] != 0) return;
-    __shared__ double scratch[33];
+// Scalar part of one LSQR step (lsqr.py:458-526): second plane rotation, norm estimates, stopping tests, state update.
+// ONE thread calls it, after every thread has taken its snapshot of the state.
+__device__ __forceinline__ void lsqr_step_tail(double* ds, int* is, double* hist, double alfa, double beta, double anorm,
+                                               double rho, double theta, double rhobar, double phi, double phibar,
+                                               double tau, double ww) {
     const double eps = 2.220446049250313e-16;
-    // every thread snapshots the scalars it needs BEFORE the first barrier; thread 0 rewrites the
-    // state only after the last one.
-    double alfa = ds[PLA_LSQR_ALFA];
-    double anorm = ds[PLA_LSQR_ANORM];
-    const double rhobar0 = ds[PLA_LSQR_RHOBAR], phibar0 = ds[PLA_LSQR_PHIBAR];
-    const double beta = sqrt(zss[n]);                    // lsqr.py:422
-    const double alfa_prev = alfa;
-
-    // ---- v = A^T u - beta v ; alfa = |v| ; v /= alfa          (lsqr.py:424-430)
-    if (beta > 0.0) {
-        double acc = 0.0;
-        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-            const double vi = t[i] / beta - beta * v[i];
-            v[i] = vi;
-            acc = fma(vi, vi, acc);
-        }
-        alfa = sqrt(block_sum(acc, scratch));
-        anorm = sqrt(anorm * anorm + alfa_prev * alfa_prev + beta * beta);
-    }
-    // ---- |w|^2 for ddnorm (lsqr.py:453-457) while w is still the old direction
-    double wacc = 0.0;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) wacc = fma(w[i], w[i], wacc);
-    const double ww = block_sum(wacc, scratch);
-
-    // ---- scalar recurrences, computed redundantly by every thread (identical results)
-    double cs, sn, rho;
-    sym_ortho(rhobar0, beta, cs, sn, rho);    // rhobar1 == rhobar (damp = 0)
-    const double theta = sn * alfa;
-    const double rhobar = -cs * alfa;
-    const double phi = cs * phibar0;
-    const double phibar = sn * phibar0;
-    const double tau = sn * phi;
-    const double t1 = phi / rho, t2 = -theta / rho;
-    const bool scale_v = (beta > 0.0) && (alfa > 0.0);
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        double vi = v[i];
-        if (scale_v) { vi = vi / alfa; v[i] = vi; }
-        const double wi = w[i];
-        x[i] = fma(t1, wi, x[i]);                          // :455
-        w[i] = fma(t2, wi, vi);                            // :456
-    }
-    if (threadIdx.x != 0) return;
-
     const double ddnorm = ds[PLA_LSQR_DDNORM] + ww / (rho * rho);
     const double cs2 = ds[PLA_LSQR_CS2], sn2 = ds[PLA_LSQR_SN2], zprev = ds[PLA_LSQR_Z];
     double xxnorm = ds[PLA_LSQR_XXNORM];
@@ -183,6 +143,238 @@ __global__ void __launch_bounds__(LS_THREADS) lsqr_step_kernel(long long n, cons
     is[PLA_LSQR_ITN] = itn;
     is[PLA_LSQR_ISTOP] = istop;
 }
+
+__global__ void __launch_bounds__(LS_THREADS) lsqr_step_kernel(long long n, const double* __restrict__ t,
+                                                               const double* __restrict__ zss, double* x, double* v,
+                                                               double* w, double* ds, int* is, double* hist) {
+    if (is[PLA_LSQR_ISTOP] != 0) return;
+    __shared__ double scratch[33];
+    // every thread snapshots the scalars it needs BEFORE the first barrier; thread 0 rewrites the
+    // state only after the last one.
+    double alfa = ds[PLA_LSQR_ALFA];
+    double anorm = ds[PLA_LSQR_ANORM];
+    const double rhobar0 = ds[PLA_LSQR_RHOBAR], phibar0 = ds[PLA_LSQR_PHIBAR];
+    const double beta = sqrt(zss[n]);                    // lsqr.py:422
+    const double alfa_prev = alfa;
+
+    // ---- v = A^T u - beta v ; alfa = |v| ; v /= alfa          (lsqr.py:424-430)
+    if (beta > 0.0) {
+        double acc = 0.0;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const double vi = t[i] / beta - beta * v[i];
+            v[i] = vi;
+            acc = fma(vi, vi, acc);
+        }
+        alfa = sqrt(block_sum(acc, scratch));
+        anorm = sqrt(anorm * anorm + alfa_prev * alfa_prev + beta * beta);
+    }
+    // ---- |w|^2 for ddnorm (lsqr.py:453-457) while w is still the old direction
+    double wacc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) wacc = fma(w[i], w[i], wacc);
+    const double ww = block_sum(wacc, scratch);
+
+    // ---- scalar recurrences, computed redundantly by every thread (identical results)
+    double cs, sn, rho;
+    sym_ortho(rhobar0, beta, cs, sn, rho);    // rhobar1 == rhobar (damp = 0)
+    const double theta = sn * alfa;
+    const double rhobar = -cs * alfa;
+    const double phi = cs * phibar0;
+    const double phibar = sn * phibar0;
+    const double tau = sn * phi;
+    const double t1 = phi / rho, t2 = -theta / rho;
+    const bool scale_v = (beta > 0.0) && (alfa > 0.0);
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        double vi = v[i];
+        if (scale_v) { vi = vi / alfa; v[i] = vi; }
+        const double wi = w[i];
+        x[i] = fma(t1, wi, x[i]);                          // :455
+        w[i] = fma(t2, wi, vi);                            // :456
+    }
+    if (threadIdx.x != 0) return;
+    lsqr_step_tail(ds, is, hist, alfa, beta, anorm, rho, theta, rhobar, phi, phibar, tau, ww);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused vector phase of one LSQR iteration for SMALL preconditioners (single GPU, delta == 0, dense M = R^{-1} or
+// V / sigma, n_in x r row-major):
+//     [z | |u~|^2] = sum of the streaming pass's per-CTA partials        (stream_pass_reduce_kernel)
+//     t = M^T z                                                          (preconditioning.py:37, pass over M)
+//     Golub-Kahan / plane-rotation step on v, w, x, stopping tests       (lsqr_step_kernel)
+//     xw = M v_new                                                       (preconditioning.py:28 of the NEXT iteration)
+// = six launches of the unfused chain, which at 2^16 x 500 cost more than the pass over A itself.  ONE thread-block
+// cluster of LF_CS CTAs does all of it: CTA c owns rows [i0, i1) of M -- the same slice of z it has just reduced, so
+// the partial of t over its rows needs no exchange -- the partials of t are summed through distributed shared memory
+// after one cluster barrier, every CTA then performs the (cheap) n-vector step redundantly with identical arithmetic,
+// so each holds the new v for its rows of M v; CTA 0 alone writes x, v, w and the state back.
+constexpr int LF_THREADS = 512;
+constexpr int LF_MAXK = 4;             // columns of M per thread: r <= LF_MAXK * LF_THREADS
+constexpr int LF_CS = 8;               // CTAs per cluster (portable maximum)
+constexpr int LF_MAX_R = LF_MAXK * LF_THREADS;
+constexpr int LF_MAX_NIN = 4096;
+
+struct FusedStepParams {
+    long long n_in, r, ldm;
+    const double* M;
+    const double* zpart;               // [nparts][n_in] partials of z = A^T u~ ;  nparts == 0: read zss instead
+    const double* sspart;              // [nparts] partials of |u~|^2
+    int nparts;
+    double* zss;                       // [n_in + 1]  written when nparts > 0, read otherwise
+    double* t;                         // [r]   (written for callers that look at it; not read)
+    double* x; double* v; double* w;   // [r]
+    double* xw;                        // [n_in] M v_new
+    double* ds; int* is; double* hist;
+};
+
+__global__ void __launch_bounds__(LF_THREADS, 1) lsqr_fused_step_kernel(const FusedStepParams p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
+    // cluster-uniform: CTA 0 rewrites the flag only after the cluster barrier below, which every CTA reaches after this read
+    if (p.is[PLA_LSQR_ISTOP] != 0) return;
+    extern __shared__ double lf_sm[];
+    const long long n_in = p.n_in, r = p.r;
+    const long long rp = (n_in + CS - 1) / CS;
+    const long long i0 = (long long)rank * rp < n_in ? (long long)rank * rp : n_in;
+    const long long i1 = i0 + rp < n_in ? i0 + rp : n_in;
+    const int nloc = (int)(i1 - i0);
+    double* zs = lf_sm;                     // [rp + 1] my slice of z, then |u~|^2 at index nloc
+    double* tp = zs + rp + 1;               // [r] partial of t over my rows of M (read by the whole cluster)
+    double* ts = tp + r;                    // [r] t
+    double* vs = ts + r;                    // [r] v (old, then new)
+    double* wsm = vs + r;                   // [r] w (old)
+    double* red = wsm + r;                  // [2][8][33]
+    double* scratch = red + 2 * 8 * 33;     // [33]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    // snapshot of everything CTA 0 will overwrite, taken before the cluster barrier
+    double alfa = p.ds[PLA_LSQR_ALFA];
+    double anorm = p.ds[PLA_LSQR_ANORM];
+    const double rhobar0 = p.ds[PLA_LSQR_RHOBAR], phibar0 = p.ds[PLA_LSQR_PHIBAR];
+    const double alfa_prev = alfa;
+    for (long long j = tid; j < r; j += LF_THREADS) { vs[j] = p.v[j]; wsm[j] = p.w[j]; }
+
+    // ---- (1) my slice of z and |u~|^2: the summation order of stream_pass_reduce_kernel (8 interleaved groups of
+    //          partials, 8-way trees, groups added in order)
+    const int nvirt = nloc + 1;
+    if (p.nparts > 0) {
+        const int half = tid >> 8, cl = lane, grp = wid & 7;
+        for (int cb = 0; cb < nvirt; cb += 64) {
+            const int lc = cb + half * 32 + cl;
+            double acc = 0.0;
+            if (lc < nvirt) {
+                const double* src = lc < nloc ? p.zpart + (i0 + lc) : p.sspart;
+                const long long stride = lc < nloc ? n_in : 1;
+                for (int b0 = grp; b0 < p.nparts; b0 += 64) {
+                    double tt[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int b = b0 + 8 * u;
+                        tt[u] = b < p.nparts ? src[(size_t)b * stride] : 0.0;
+                    }
+                    acc += ((tt[0] + tt[1]) + (tt[2] + tt[3])) + ((tt[4] + tt[5]) + (tt[6] + tt[7]));
+                }
+            }
+            red[(half * 8 + grp) * 33 + cl] = acc;
+            __syncthreads();
+            if (grp == 0 && lc < nvirt) {
+                double tot = 0.0;
+#pragma unroll
+                for (int g2 = 0; g2 < 8; ++g2) tot += red[(half * 8 + g2) * 33 + cl];
+                zs[lc] = tot;
+                if (lc < nloc) p.zss[i0 + lc] = tot;
+                else if (rank == 0) p.zss[n_in] = tot;
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int lc = tid; lc < nvirt; lc += LF_THREADS) zs[lc] = lc < nloc ? p.zss[i0 + lc] : p.zss[n_in];
+        __syncthreads();
+    }
+    const double beta = sqrt(zs[nloc]);                  // lsqr.py:422
+
+    // ---- (2) partial of t = M^T z over my rows: thread <-> columns tid + 512 k
+    {
+        double acc[LF_MAXK];
+#pragma unroll
+        for (int k = 0; k < LF_MAXK; ++k) acc[k] = 0.0;
+        const int kc = (int)((r + LF_THREADS - 1) / LF_THREADS);
+#pragma unroll 8
+        for (int i = 0; i < nloc; ++i) {
+            const double zi = zs[i];
+            const double* __restrict__ row = p.M + (i0 + i) * p.ldm;
+#pragma unroll
+            for (int k = 0; k < LF_MAXK; ++k) {
+                const long long j = tid + (long long)k * LF_THREADS;
+                if (k < kc && j < r) acc[k] = fma(__ldg(row + j), zi, acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < LF_MAXK; ++k) {
+            const long long j = tid + (long long)k * LF_THREADS;
+            if (j < r) tp[j] = acc[k];
+        }
+    }
+    cluster.sync();
+    // ---- (3) t = sum of the cluster's partials, in CTA order (identical in every CTA)
+    for (long long j = tid; j < r; j += LF_THREADS) {
+        double part[LF_CS];
+#pragma unroll
+        for (int c = 0; c < LF_CS; ++c) part[c] = c < CS ? cluster.map_shared_rank(tp, c)[j] : 0.0;
+        double tot = 0.0;
+#pragma unroll
+        for (int c = 0; c < LF_CS; ++c) tot += part[c];
+        ts[j] = tot;
+        if (rank == 0) p.t[j] = tot;
+    }
+
+    // ---- (4) the step of lsqr_step_kernel on the shared-memory copies (thread j touches only its own entries)
+    if (beta > 0.0) {
+        double acc = 0.0;
+        for (long long i = tid; i < r; i += LF_THREADS) {
+            const double vi = ts[i] / beta - beta * vs[i];
+            vs[i] = vi;
+            acc = fma(vi, vi, acc);
+        }
+        alfa = sqrt(block_sum(acc, scratch));
+        anorm = sqrt(anorm * anorm + alfa_prev * alfa_prev + beta * beta);
+    }
+    double wacc = 0.0;
+    for (long long i = tid; i < r; i += LF_THREADS) wacc = fma(wsm[i], wsm[i], wacc);
+    const double ww = block_sum(wacc, scratch);
+    double cs, sn, rho;
+    sym_ortho(rhobar0, beta, cs, sn, rho);
+    const double theta = sn * alfa;
+    const double rhobar = -cs * alfa;
+    const double phi = cs * phibar0;
+    const double phibar = sn * phibar0;
+    const double tau = sn * phi;
+    const double t1 = phi / rho, t2 = -theta / rho;
+    const bool scale_v = (beta > 0.0) && (alfa > 0.0);
+    for (long long i = tid; i < r; i += LF_THREADS) {
+        double vi = vs[i];
+        if (scale_v) { vi = vi / alfa; vs[i] = vi; }
+        if (rank == 0) {
+            const double wi = wsm[i];
+            p.v[i] = vi;
+            p.x[i] = fma(t1, wi, p.x[i]);
+            p.w[i] = fma(t2, wi, vi);
+        }
+    }
+    if (rank == 0 && tid == 0)
+        lsqr_step_tail(p.ds, p.is, p.hist, alfa, beta, anorm, rho, theta, rhobar, phi, phibar, tau, ww);
+    __syncthreads();                                     // vs complete
+
+    // ---- (5) xw = M v_new on my rows: warp <-> row
+    for (int i = wid; i < nloc; i += LF_THREADS / 32) {
+        const double* __restrict__ row = p.M + (i0 + i) * p.ldm;
+        double acc = 0.0;
+#pragma unroll 8
+        for (long long j = lane; j < r; j += 32) acc = fma(__ldg(row + j), vs[j], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) p.xw[i0 + i] = acc;
+    }
+    cluster.sync();                                      // no CTA may exit while another can still read its tp
+}
+
 
 __global__ void __launch_bounds__(LS_THREADS) lsqr_ridge_kernel(long long n, double sd, const double* __restrict__ xw,
                                                                 double* ub, const double* sc, double sa, double su,
@@ -425,6 +617,35 @@ extern "C" int pla_lsqr_step_f64(int64_t n, const double* t, const double* zss, 
     PLA_CHECK_ARG(x && v && w && dstate && istate && arnorm_hist, 4, "null state");
     lsqr_step_kernel<<<1, LS_THREADS, 0, (cudaStream_t)stream>>>(n, t, zss, x, v, w, dstate, istate, arnorm_hist);
     PLA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int pla_lsqr_fused_step_f64(int64_t n_in, int64_t r, const double* M, int64_t ldm, const double* pass_ws,
+                                       int64_t nparts, int64_t ss_offset, double* zss, double* t, double* x, double* v,
+                                       double* w, double* xw, double* dstate, int* istate, double* arnorm_hist,
+                                       void* stream) {
+    PLA_CHECK_ARG(n_in >= 1 && n_in <= LF_MAX_NIN, 1, "n_in out of range (1..4096)");
+    PLA_CHECK_ARG(r >= 1 && r <= LF_MAX_R, 2, "r out of range (1..2048)");
+    PLA_CHECK_ARG(M != nullptr && ldm >= r, 4, "M is null or ldm < r");
+    PLA_CHECK_ARG(nparts >= 0 && nparts <= (1 << 20) && (nparts == 0 || (pass_ws != nullptr && ss_offset >= nparts * n_in)), 6,
+                  "bad partials (nparts, ss_offset)");
+    PLA_CHECK_ARG(zss && t && x && v && w && xw, 8, "null vector");
+    PLA_CHECK_ARG(dstate && istate && arnorm_hist, 14, "null state");
+    FusedStepParams p;
+    p.n_in = n_in; p.r = r; p.ldm = ldm; p.M = M;
+    p.zpart = pass_ws; p.sspart = pass_ws ? pass_ws + ss_offset : nullptr; p.nparts = (int)nparts;
+    p.zss = zss; p.t = t; p.x = x; p.v = v; p.w = w; p.xw = xw; p.ds = dstate; p.is = istate; p.hist = arnorm_hist;
+    const long long rp = (n_in + LF_CS - 1) / LF_CS;
+    const size_t smem = ((size_t)rp + 1 + 4 * (size_t)r + 2 * 8 * 33 + 33) * sizeof(double);
+    PLA_CUDA(cudaFuncSetAttribute(lsqr_fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(LF_CS); cfg.blockDim = dim3(LF_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = LF_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PLA_CUDA(cudaLaunchKernelEx(&cfg, lsqr_fused_step_kernel, p));
+    note_launch();
     return 0;
 }
 

@@ -379,7 +379,14 @@ static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts
     const size_t budget = 200 * 1024;
     int stages = (int)(budget / stage_bytes);
     if (stages > SP_MAX_STAGES) stages = SP_MAX_STAGES;
-    if (stages < 2) return cudaErrorInvalidValue;
+    // The ring length must be a multiple of the number of consumer groups: tile q lives in stage q % S and belongs to
+    // group q % NG, so only then does every stage always meet the SAME group, which sees each of its completions.
+    // Otherwise a group meets a stage every second fill and waits on one parity for ever: a warp that runs a few
+    // tiles ahead (nothing holds the warps of a group together when no row sums are exchanged, flags = AXPY only)
+    // takes the completion of an older fill for its own, reads a stale tile and arrives twice on the stage's
+    // `empty` barrier -- a launch failure at 65536 x 500 (4 groups, 6 stages) before this rule.
+    stages = stages / NG * NG;
+    if (stages < 2 || stages < NG) return cudaErrorInvalidValue;
     p.stages = stages;
     p.ntiles = (p.m + RT - 1) / RT;
     p.use_tma = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
@@ -416,9 +423,12 @@ extern "C" size_t pla_stream_pass_workspace_bytes(int64_t m, int64_t n) {
     return (size_t)num_sms() * SP_MAX_GROUPS * (size_t)(n + 1) * sizeof(double) + 256;
 }
 
+// parts_out != nullptr: the reduce kernel is NOT launched; the per-(CTA, group) partials stay in `ws` and
+// parts_out = {number of partials, offset (in doubles) of the |u|^2 partials inside ws} (pla_stream_pass_parts_f64).
 static int stream_pass_impl(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
                             const double* g, const double* sc_dev, double sa, double su, double* zss,
-                            int flags, const int* istop_dev, void* ws, size_t ws_bytes, void* stream, const PeerExchange& px) {
+                            int flags, const int* istop_dev, void* ws, size_t ws_bytes, void* stream, const PeerExchange& px,
+                            int64_t* parts_out = nullptr) {
     PLA_CHECK_ARG(A != nullptr, 1, "A is null");
     PLA_CHECK_ARG(m >= 1, 2, "m < 1");
     PLA_CHECK_ARG(n >= 1 && n <= PLA_PASS_MAX_N, 3, "n out of range for the streaming pass (1..8192)");
@@ -427,7 +437,7 @@ static int stream_pass_impl(const double* A, int64_t m, int64_t n, int64_t lda, 
     PLA_CHECK_ARG(!do_dot || (w != nullptr && u != nullptr), 5, "DOT needs w and u");
     PLA_CHECK_ARG(do_dot || u != nullptr || (flags & PLA_PASS_AXPY_G), 6, "u is null");
     PLA_CHECK_ARG(!(flags & PLA_PASS_AXPY_G) || g != nullptr, 7, "AXPY_G needs g");
-    PLA_CHECK_ARG(zss != nullptr, 11, "zss is null");
+    PLA_CHECK_ARG(zss != nullptr || parts_out != nullptr, 11, "zss is null");
     PLA_CHECK_ARG(ws != nullptr && ws_bytes >= pla_stream_pass_workspace_bytes(m, n), 15, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -473,6 +483,11 @@ static int stream_pass_impl(const double* A, int64_t m, int64_t n, int64_t lda, 
     }
 #undef PLA_SP_CASE
     if (e != cudaSuccess) { set_error("pla_stream_pass_f64: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    if (parts_out != nullptr) {
+        parts_out[0] = nparts;
+        parts_out[1] = (int64_t)(p.sspart - p.zpart);
+        return 0;
+    }
     const int rb = (int)((n + 1 + SPR_COLS - 1) / SPR_COLS);
     stream_pass_reduce_kernel<<<rb, SPR_COLS * SPR_WARPS, 0, st>>>(p.zpart, p.sspart, nparts, n, zss, do_axpy ? 1 : 0,
                                                                   istop_dev, px);
@@ -486,6 +501,16 @@ extern "C" int pla_stream_pass_f64(const double* A, int64_t m, int64_t n, int64_
     PeerExchange px;
     memset(&px, 0, sizeof(px));
     return stream_pass_impl(A, m, n, lda, w, u, g, sc_dev, sa, su, zss, flags, istop_dev, ws, ws_bytes, stream, px);
+}
+
+extern "C" int pla_stream_pass_parts_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,
+                                         const double* g, const double* sc_dev, double sa, double su, int flags,
+                                         const int* istop_dev, void* ws, size_t ws_bytes, int64_t* parts_out, void* stream) {
+    PLA_CHECK_ARG(parts_out != nullptr, 15, "parts_out is null");
+    PeerExchange px;
+    memset(&px, 0, sizeof(px));
+    return stream_pass_impl(A, m, n, lda, w, u, g, sc_dev, sa, su, nullptr, flags, istop_dev, ws, ws_bytes, stream, px,
+                            parts_out);
 }
 
 extern "C" int pla_stream_pass_peer_f64(const double* A, int64_t m, int64_t n, int64_t lda, const double* w, double* u,

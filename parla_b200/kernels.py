@@ -136,6 +136,37 @@ def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None,
     return zss
 
 
+_PARTS_OUT = (ctypes.c_int64 * 2)()
+FUSED_MAX_R, FUSED_MAX_NIN = 2048, 4096      # limits of pla_lsqr_fused_step_f64
+
+
+def stream_pass_parts(A, *, w, u, sc=None, sa=1.0, su=0.0, flags=PASS_DOT | PASS_AXPY, istop=None):
+    """The streaming pass WITHOUT its reduce launch (pla_stream_pass_parts_f64): returns (workspace, number of
+    partials, offset of the |u|^2 partials) for :func:`lsqr_fused_step`.  Narrow / even-n shapes only (the caller
+    checks: no column blocks, no peer exchange)."""
+    lib = _lib.load()
+    A, lda = _rowmajor(A, "A")
+    m, n = A.shape
+    ws = Workspace.get(A.device, lib.pla_stream_pass_workspace_bytes(m, n), "pass")
+    rc = lib.pla_stream_pass_parts_f64(A.data_ptr(), m, n, lda, _p(w), _p(u), None, _p(sc), float(sa), float(su),
+                                       int(flags), _p(istop), ws.data_ptr(), ws.numel(),
+                                       ctypes.addressof(_PARTS_OUT), _stream())
+    _lib.check(rc, "pla_stream_pass_parts_f64")
+    return ws, int(_PARTS_OUT[0]), int(_PARTS_OUT[1])
+
+
+def lsqr_fused_step(M, ws, nparts, ss_offset, zss, t, x, v, w, xw, dstate, istate, hist):
+    """Reduce of the pass's partials, t = M^T z, the LSQR step and xw = M v_new in one cluster launch
+    (pla_lsqr_fused_step_f64).  ``ws`` None / nparts 0: z and |u|^2 are taken from ``zss`` instead."""
+    M, ldm = _rowmajor(M, "M")
+    n_in, r = M.shape
+    rc = _lib.load().pla_lsqr_fused_step_f64(n_in, r, M.data_ptr(), ldm, _p(ws), int(nparts), int(ss_offset),
+                                             zss.data_ptr(), t.data_ptr(), x.data_ptr(), v.data_ptr(), w.data_ptr(),
+                                             xw.data_ptr(), dstate.data_ptr(), istate.data_ptr(), hist.data_ptr(),
+                                             _stream())
+    _lib.check(rc, "pla_lsqr_fused_step_f64")
+
+
 WIDE_BLOCK = 4096       # column-block width of the wide-matrix path (even, so every block keeps 16-byte aligned rows)
 
 

@@ -67,6 +67,25 @@ def test_stream_pass_modes_and_device_scalars(K):
     assert torch.equal(r2.cpu(), torch.from_numpy(b))
 
 
+@pytest.mark.parametrize("m,n", [(65536, 500), (40000, 300), (30000, 1000), (50000, 77), (20000, 2048), (9000, 2049)])
+def test_stream_pass_single_product_modes_on_tall_matrices(K, m, n):
+    """A^T u alone (adjoint_pass, rmatvec: no row sums, so nothing holds the warps of a consumer group together) and
+    A w alone, with many ring wraps per CTA.  65536 x 500 (4 consumer groups, 6 stages) used to fail: a group met a
+    stage only on every second fill and took an older completion for its own (csrc/stream_pass.cu, launch_pass)."""
+    g = torch.Generator(device="cuda").manual_seed(m + n)
+    A = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    u = torch.randn(m, dtype=torch.float64, device="cuda", generator=g)
+    w = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    for _ in range(3):
+        zss = K.stream_pass(A, u=u, flags=K.PASS_AXPY)
+        ref = A.T @ u
+        assert float(torch.linalg.vector_norm(zss[:n] - ref)) <= 1e-12 * float(torch.linalg.vector_norm(ref))
+        assert abs(float(zss[n]) - float(u @ u)) <= 1e-12 * float(u @ u)
+        y, zs2 = K.matvec(A, w)
+        ref = A @ w
+        assert float(torch.linalg.vector_norm(y - ref)) <= 1e-12 * float(torch.linalg.vector_norm(ref))
+
+
 def test_stream_pass_strided_and_unaligned(K):
     rng = np.random.default_rng(6)
     big = rng.standard_normal((400, 130))
