@@ -40,6 +40,7 @@ struct StreamPassParams {
     const int* istop;
     int flags;
     int stages;
+    int use_tag;            // 1: consumers check the stage's tile tag after the wait (ring length not a multiple of the groups)
     int use_tma;            // 1: 16B-aligned row tiles -- one bulk copy per tile (lda == n) or per row (lda > n)
     long long ntiles;
 };
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
     double* red = reinterpret_cast<double*>(empty + SP_MAX_STAGES);     // [groups][2][8 warps][RMAX]
     double* ustage = red + SP_MAX_GROUPS * 2 * (SP_GROUP_MAX / 32) * SP_RMAX;   // [stages][RMAX]  old u of the tile rows
     double* gstage = ustage + SP_MAX_STAGES * SP_RMAX;                  // [stages][RMAX]  g of the tile rows
+    long long* tag = reinterpret_cast<long long*>(gstage + SP_MAX_STAGES * SP_RMAX);   // [stages] tile held / being loaded
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1 + 32); mbar_init(&empty[s], NW); }
@@ -98,12 +100,16 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
             if (tma_ok) {
                 if (p.lda == n) {
                     if (lane == 0) {
+                        *reinterpret_cast<volatile long long*>(tag + s) = t;      // (released by the arrive below)
                         mbar_arrive_expect_tx(&full[s], (uint32_t)(elems * 8));
                         bulk_g2s(dst, p.A + r0 * p.lda, (uint32_t)(elems * 8), &full[s], pol);
                     }
                 } else {
                     // a column block / padded matrix: rows are 16-byte aligned pieces, one bulk copy each
-                    if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(elems * 8));
+                    if (lane == 0) {
+                        *reinterpret_cast<volatile long long*>(tag + s) = t;
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(elems * 8));
+                    }
                     __syncwarp();
                     if (lane < rows)
                         bulk_g2s(dst + (size_t)lane * n, p.A + (r0 + lane) * p.lda, (uint32_t)(n * 8), &full[s], pol);
@@ -115,7 +121,10 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
                     for (long long c = lane; c < n; c += 32) dst[(size_t)r * n + c] = __ldg(src + c);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+                if (lane == 0) {
+                    *reinterpret_cast<volatile long long*>(tag + s) = t;
+                    mbar_arrive(&full[s]);
+                }
             }
             if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -150,6 +159,12 @@ __global__ void __launch_bounds__(NG * GS + 32, 1) stream_pass_kernel(const Stre
         const long long r0 = t * RT;
         const int rows = (int)min((long long)RT, p.m - r0);
         mbar_wait(&full[s], ph);
+        // S % NG != 0: this group meets stage s only on every NG / gcd(S, NG)-th fill and always waits on the same
+        // parity, so the completion of an OLDER fill can satisfy the wait (a parity wait must see every phase).  The
+        // producer tags the stage with the tile it is loading before it arrives on `full`; once the tag is ours the
+        // stage is in the phase we wait for and the wait is exact.  Until then: spin (at most one fill time).
+        if (p.use_tag)
+            while (*reinterpret_cast<volatile long long*>(tag + s) != t) mbar_wait(&full[s], ph);
         const double* tile = tiles + (size_t)s * stage_elems;
         const double* uo = ustage + s * SP_RMAX;           // old u / g of the tile rows (broadcast reads)
         const double* gq = gstage + s * SP_RMAX;
@@ -379,14 +394,15 @@ static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts
     const size_t budget = 200 * 1024;
     int stages = (int)(budget / stage_bytes);
     if (stages > SP_MAX_STAGES) stages = SP_MAX_STAGES;
-    // The ring length must be a multiple of the number of consumer groups: tile q lives in stage q % S and belongs to
-    // group q % NG, so only then does every stage always meet the SAME group, which sees each of its completions.
-    // Otherwise a group meets a stage every second fill and waits on one parity for ever: a warp that runs a few
-    // tiles ahead (nothing holds the warps of a group together when no row sums are exchanged, flags = AXPY only)
-    // takes the completion of an older fill for its own, reads a stale tile and arrives twice on the stage's
-    // `empty` barrier -- a launch failure at 65536 x 500 (4 groups, 6 stages) before this rule.
-    stages = stages / NG * NG;
+    // Tile q lives in stage q % S and belongs to group q % NG.  Unless S is a multiple of NG a group meets a stage
+    // only on every second (or fourth) fill and always waits on the same parity, so it can take the completion of an
+    // OLDER fill for its own, read a stale tile and arrive twice on the stage's `empty` barrier (A^T u alone at
+    // 65536 x 500 -- 4 groups, 6 stages, fast consumers -- died with a launch failure).  Default: keep the deepest
+    // ring and let the consumers verify the stage's tile tag (use_tag); PLA_PASS_TAGS=0: round S down instead.
+    static const bool tags = [] { const char* e = getenv("PLA_PASS_TAGS"); return !(e && e[0] == '0'); }();
+    if (!tags) stages = stages / NG * NG;
     if (stages < 2 || stages < NG) return cudaErrorInvalidValue;
+    p.use_tag = (stages % NG != 0) ? 1 : 0;
     p.stages = stages;
     p.ntiles = (p.m + RT - 1) / RT;
     p.use_tma = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
@@ -395,7 +411,7 @@ static cudaError_t launch_pass(StreamPassParams& p, cudaStream_t st, int* nparts
     if ((long long)grid > p.ntiles) grid = (int)p.ntiles;
     *nparts = grid * NG;
     const size_t smem = (((size_t)stages * stage_bytes + 15) & ~(size_t)15) + 2 * SP_MAX_STAGES * 8 +
-                        SP_MAX_GROUPS * 2 * (SP_GROUP_MAX / 32) * SP_RMAX * 8 + 2 * SP_MAX_STAGES * SP_RMAX * 8;
+                        SP_MAX_GROUPS * 2 * (SP_GROUP_MAX / 32) * SP_RMAX * 8 + 2 * SP_MAX_STAGES * SP_RMAX * 8 + SP_MAX_STAGES * 8;
     cudaError_t e = cudaFuncSetAttribute(stream_pass_kernel<VEC, J, NG, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
