@@ -136,7 +136,6 @@ def stream_pass(A, *, w=None, u=None, g=None, sc=None, sa=1.0, su=0.0, zss=None,
     return zss
 
 
-_PARTS_OUT = (ctypes.c_int64 * 2)()
 FUSED_MAX_R, FUSED_MAX_NIN = 2048, 4096      # limits of pla_lsqr_fused_step_f64
 
 
@@ -148,11 +147,12 @@ def stream_pass_parts(A, *, w, u, sc=None, sa=1.0, su=0.0, flags=PASS_DOT | PASS
     A, lda = _rowmajor(A, "A")
     m, n = A.shape
     ws = Workspace.get(A.device, lib.pla_stream_pass_workspace_bytes(m, n), "pass")
+    parts = (ctypes.c_int64 * 2)()
     rc = lib.pla_stream_pass_parts_f64(A.data_ptr(), m, n, lda, _p(w), _p(u), None, _p(sc), float(sa), float(su),
                                        int(flags), _p(istop), ws.data_ptr(), ws.numel(),
-                                       ctypes.addressof(_PARTS_OUT), _stream())
+                                       ctypes.addressof(parts), _stream())
     _lib.check(rc, "pla_stream_pass_parts_f64")
-    return ws, int(_PARTS_OUT[0]), int(_PARTS_OUT[1])
+    return ws, int(parts[0]), int(parts[1])
 
 
 def lsqr_fused_step(M, ws, nparts, ss_offset, zss, t, x, v, w, xw, dstate, istate, hist):

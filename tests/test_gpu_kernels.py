@@ -67,11 +67,12 @@ def test_stream_pass_modes_and_device_scalars(K):
     assert torch.equal(r2.cpu(), torch.from_numpy(b))
 
 
-@pytest.mark.parametrize("m,n", [(65536, 500), (40000, 300), (30000, 1000), (50000, 77), (20000, 2048), (9000, 2049)])
+@pytest.mark.parametrize("m,n", [(65536, 500), (40000, 300), (30000, 1000), (50000, 77), (20000, 2048), (9000, 2049),
+                                 (30000, 1700), (60000, 256)])
 def test_stream_pass_single_product_modes_on_tall_matrices(K, m, n):
     """A^T u alone (adjoint_pass, rmatvec: no row sums, so nothing holds the warps of a consumer group together) and
     A w alone, with many ring wraps per CTA.  65536 x 500 (4 consumer groups, 6 stages) used to fail: a group met a
-    stage only on every second fill and took an older completion for its own (csrc/stream_pass.cu, launch_pass)."""
+    stage only on every second fill and took an older completion for its own (csrc/stream_pass.cu: stage tags).  1700 columns: 2 groups on a 7-stage ring."""
     g = torch.Generator(device="cuda").manual_seed(m + n)
     A = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
     u = torch.randn(m, dtype=torch.float64, device="cuda", generator=g)
@@ -84,6 +85,12 @@ def test_stream_pass_single_product_modes_on_tall_matrices(K, m, n):
         y, zs2 = K.matvec(A, w)
         ref = A @ w
         assert float(torch.linalg.vector_norm(y - ref)) <= 1e-12 * float(torch.linalg.vector_norm(ref))
+        u2 = u.clone()                                    # both products in one read (every ring shape with tags)
+        zss = K.stream_pass(A, w=w, u=u2, sa=0.5, su=-1.0, flags=K.PASS_DOT | K.PASS_AXPY)
+        uref = 0.5 * ref - u
+        zref = A.T @ uref
+        assert float(torch.linalg.vector_norm(u2 - uref)) <= 1e-12 * float(torch.linalg.vector_norm(uref))
+        assert float(torch.linalg.vector_norm(zss[:n] - zref)) <= 1e-12 * float(torch.linalg.vector_norm(zref))
 
 
 def test_stream_pass_strided_and_unaligned(K):
