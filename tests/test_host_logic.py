@@ -235,3 +235,23 @@ def test_procedural_wrappers_and_utils_exist():
     assert list(inspect.signature(aware.rs1).parameters)[:4] == ["A", "k", "num_pass", "rng"]
     for name in ("orth", "lu_stabilize", "lupt", "lup", "apply_pinv_on_left", "apply_pinv_on_right"):
         assert callable(getattr(ulaw, name))
+
+
+def test_fused_vector_phase_is_selected_only_where_it_applies():
+    """comps/determiter/lsqr.py takes the fused path (pla_stream_pass_parts_f64 + pla_lsqr_fused_step_f64) only for a
+    small dense row-major preconditioner on one GPU without ridge rows; everything else keeps the eager chain."""
+    from parla_b200.comps.preconditioning import PrecondOperator
+    from parla_b200.comps.determiter import lsqr as lsqr_mod
+    A = torch.zeros(50, 12, dtype=torch.float64)
+    M = torch.eye(12, dtype=torch.float64)
+    cap = lsqr_mod.FUSED_MAX_ELEMS
+    assert cap == 1 << 20 or "PLA_LSQR_FUSED_MAX_ELEMS" in os.environ
+    assert PrecondOperator(A, 0.0, M, False).fusable(cap)
+    assert not PrecondOperator(A, 0.0, M, True).fusable(cap)                     # triangular solves, not a dense M
+    assert not PrecondOperator(A, 0.5, M, False).fusable(cap)                    # ridge rows
+    assert PrecondOperator(A, 0.0, M[:, :7].contiguous(), False).fusable(cap)    # rank-truncated (svd mode)
+    assert not PrecondOperator(A, 0.0, M.T.contiguous().T, False).fusable(cap)   # column-major M
+    assert not PrecondOperator(A, 0.0, M, False).fusable(100)                    # too large for eight SMs
+    wide = torch.zeros(4, 5000, dtype=torch.float64)
+    assert not PrecondOperator(wide, 0.0, torch.zeros(5000, 200, dtype=torch.float64), False).fusable(cap)   # n_in > 4096
+    assert PrecondOperator(wide[:, :3000], 0.0, torch.zeros(3000, 300, dtype=torch.float64), False).fusable(cap)
