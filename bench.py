@@ -564,8 +564,13 @@ def run_gpu_arm(a):
     torch.cuda.empty_cache()
 
     if not a.no_extras:
-        extras["strong"] = strong_record(rla, K, a, rank, world, dev, barrier, dist)
-        extras["parity"] = parity_record(rla, rank, world, dev)
+        # sub-records outside the headline timing: a failure in one of them must not cost the headline line
+        for key, fn in (("strong", lambda: strong_record(rla, K, a, rank, world, dev, barrier, dist)),
+                        ("parity", lambda: parity_record(rla, rank, world, dev))):
+            try:
+                extras[key] = fn()
+            except Exception as exc:                                   # noqa: BLE001
+                extras[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank != 0:
         if world > 1:

@@ -103,7 +103,7 @@ class PeerComm:
             self.close()
 
     def next_epoch(self):
-        self.epoch += 1
+        self.epoch = self.epoch % 0xFFFFFFFF + 1        # 1 .. 2^32 - 1: the flag is 32 bits wide and 0 means "never written"
         return self.epoch
 
     def close(self):
