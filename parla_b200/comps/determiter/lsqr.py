@@ -118,10 +118,11 @@ def lsqr(A, b, damp=0.0, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=None, show=F
 
     fused = USE_FUSED and A.fusable(FUSED_MAX_ELEMS)
 
+    fused_step = K.FusedIteration(A.A, A.R, xw, u, sc, istop_dev, zss, t, x, v, w, dstate, istate, hist) if fused else None
+
     def iteration_fused():              # xw = M v is already there: the previous fused step (or the prologue) left it
-        ws, nparts, ss_off = K.stream_pass_parts(A.A, w=xw, u=u, sc=sc, istop=istop_dev)
+        fused_step()
         A.passes += 1
-        K.lsqr_fused_step(A.R, ws, nparts, ss_off, zss, t, x, v, w, xw, dstate, istate, hist)
 
     post(0)
     events[0].synchronize()

@@ -167,6 +167,46 @@ def lsqr_fused_step(M, ws, nparts, ss_offset, zss, t, x, v, w, xw, dstate, istat
     _lib.check(rc, "pla_lsqr_fused_step_f64")
 
 
+class FusedIteration:
+    """The two launches of a fused LSQR iteration (:func:`stream_pass_parts` then :func:`lsqr_fused_step`) with their
+    argument lists built ONCE: every buffer of the iteration is fixed, so the per-iteration host work is two ctypes
+    calls instead of two wrappers (~17 us less per iteration, which matters when an iteration is ~60 us of GPU time).
+    Calls made on another stream than the one it was built on (a CUDA-graph capture) go through the wrappers."""
+
+    def __init__(self, A, M, xw, u, sc, istop, zss, t, x, v, w, dstate, istate, hist):
+        self.lib = _lib.load()
+        self.A, lda = _rowmajor(A, "A")
+        self.M, ldm = _rowmajor(M, "M")
+        m, n = self.A.shape
+        n_in, r = self.M.shape
+        self.stream = _stream()
+        self.ws = Workspace.get(self.A.device, self.lib.pla_stream_pass_workspace_bytes(m, n), "pass")
+        self.parts = (ctypes.c_int64 * 2)()
+        self.keep = (xw, u, sc, istop, zss, t, x, v, w, dstate, istate, hist)       # keeps every buffer alive
+        self.args_pass = (self.A.data_ptr(), m, n, lda, xw.data_ptr(), u.data_ptr(), None, _p(sc), 1.0, 0.0,
+                          int(PASS_DOT | PASS_AXPY), _p(istop), self.ws.data_ptr(), self.ws.numel(),
+                          ctypes.addressof(self.parts), self.stream)
+        self.head_step = (n_in, r, self.M.data_ptr(), ldm, self.ws.data_ptr())
+        self.tail_step = (zss.data_ptr(), t.data_ptr(), x.data_ptr(), v.data_ptr(), w.data_ptr(), xw.data_ptr(),
+                          dstate.data_ptr(), istate.data_ptr(), hist.data_ptr(), self.stream)
+        self.args_step = None
+
+    def __call__(self):
+        if _stream() != self.stream:
+            xw, u, sc, istop, zss, t, x, v, w, dstate, istate, hist = self.keep
+            ws, nparts, ss_off = stream_pass_parts(self.A, w=xw, u=u, sc=sc, istop=istop)
+            lsqr_fused_step(self.M, ws, nparts, ss_off, zss, t, x, v, w, xw, dstate, istate, hist)
+            return
+        rc = self.lib.pla_stream_pass_parts_f64(*self.args_pass)
+        if rc != 0:
+            _lib.check(rc, "pla_stream_pass_parts_f64")
+        if self.args_step is None:          # (the partial count of a shape never changes)
+            self.args_step = self.head_step + (int(self.parts[0]), int(self.parts[1])) + self.tail_step
+        rc = self.lib.pla_lsqr_fused_step_f64(*self.args_step)
+        if rc != 0:
+            _lib.check(rc, "pla_lsqr_fused_step_f64")
+
+
 WIDE_BLOCK = 4096       # column-block width of the wide-matrix path (even, so every block keeps 16-byte aligned rows)
 
 
